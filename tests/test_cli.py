@@ -1,0 +1,40 @@
+"""End-to-end CLI: prepare (synthetic) → launch → resume with the same rundir → sample."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, **kw):
+    env = dict(os.environ, WANDB_MODE="disabled", PYTHONPATH=ROOT)
+    env.pop("RANK", None); env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable] + args, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600, **kw)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_prepare_launch_resume_sample(tmp_path):
+    data = tmp_path / "data"
+    _run(["data/shakespeare_char/prepare.py", "--synthetic", "--out", str(data)])
+    assert (data / "train.bin").exists() and (data / "meta.pkl").exists()
+    run = tmp_path / "run"
+    common = ["launch.py", "--config=shakespeare_char", f"--rundir={run}", "--device=cpu",
+              f"--set=data_dir={data}", "--set=model_config.n_layer=2", "--set=model_config.n_embd=32",
+              "--set=model_config.n_head=2", "--set=model_config.block_size=32", "--set=batch_size=4",
+              "--set=eval_interval=3", "--set=compute_dtype=float32", "--set=debug=false"]
+    out = _run(common + ["--max_steps=4"])
+    assert "Model has" in out
+    cfgj = json.load(open(run / "config.json"))
+    assert cfgj["model_config"]["n_layer"] == 2
+    wid = open(run / "wandb_id.txt").read()
+    assert (run / "3" / "default" / "checkpoint").exists()
+    lines = [json.loads(l) for l in open(run / "metrics.jsonl")]
+    assert any("loss/val" in l for l in lines) and any("loss/optimized" in l for l in lines)
+    out2 = _run(common + ["--max_steps=7"])
+    assert "resumed from step 3" in out2
+    assert open(run / "wandb_id.txt").read() == wid
+    assert (run / "6" / "default" / "checkpoint").exists() and not (run / "3").exists()   # max_to_keep=1
+    out3 = _run(["sample.py", f"--ckpt_dir={run}", "--num_samples=2", "--max_new_tokens=8", "--device=cpu"])
+    assert out3.count("---------------") == 2

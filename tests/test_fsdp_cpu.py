@@ -1,0 +1,66 @@
+"""FSDP (gloo, world_size=2, CPU) ≡ single process: losses and post-step parameters (BASELINE config 1 plumbing)."""
+import dataclasses
+
+import pytest
+import torch
+
+from midgpt_b200 import load_config
+from midgpt_b200.config import GPTConfig
+from tests._mp import run_distributed
+
+
+def _tiny_cfg(shard_model=True, gather_mode="step", g=2, dropout=0.0):
+    cfg = load_config("shakespeare_char")
+    cfg.model_config = GPTConfig(block_size=16, vocab_size=65, n_layer=3, n_head=2, n_embd=32, dropout=dropout)
+    cfg.batch_size, cfg.g_accum_iters, cfg.shard_model = 4, g, shard_model
+    cfg.warmup_steps, cfg.lr_decay_steps, cfg.max_steps = 2, 20, 20
+    cfg.compute_dtype = "float32"
+    cfg.engine.gather_mode = gather_mode
+    cfg.engine.micro_batch_size = 1
+    return cfg
+
+
+def _batches(cfg, n_steps):
+    g = torch.Generator().manual_seed(123)
+    T, N = cfg.model_config.block_size, cfg.batch_size * cfg.g_accum_iters
+    return [(torch.randint(0, 65, (N, T), generator=g, dtype=torch.int32),
+             torch.randint(0, 65, (N, T), generator=g, dtype=torch.int32)) for _ in range(n_steps)]
+
+
+def _run(rank, world, shard_model, gather_mode, n_steps):
+    from midgpt_b200.train import Trainer
+    torch.manual_seed(0)
+    cfg = _tiny_cfg(shard_model, gather_mode)
+    tr = Trainer(cfg, device_type="cpu")
+    losses = []
+    for x, y in _batches(cfg, n_steps):
+        # global batch → this rank's slice of every accumulation step
+        G, B, T = cfg.g_accum_iters, cfg.batch_size, cfg.model_config.block_size
+        xs = x.view(G, B, T)[:, rank * B // world:(rank + 1) * B // world].reshape(-1, T)
+        ys = y.view(G, B, T)[:, rank * B // world:(rank + 1) * B // world].reshape(-1, T)
+        losses.append(tr.train_step(xs, ys).item())
+    state = {k: v.clone() for k, v in tr.engine.full_state("master").items()}
+    return losses, state, tr.engine.last_grad_norm.item()
+
+
+@pytest.mark.parametrize("shard_model,gather_mode", [(True, "step"), (True, "layer"), (False, "step")])
+def test_fsdp_ws2_equals_single(shard_model, gather_mode):
+    n_steps = 4
+    ref_losses, ref_state, ref_gn = _run(0, 1, False, "step", n_steps)
+    outs = run_distributed(_run, 2, shard_model, gather_mode, n_steps)
+    for losses, state, gn in outs:
+        assert torch.allclose(torch.tensor(losses), torch.tensor(ref_losses), rtol=1e-5, atol=1e-6)
+        assert abs(gn - ref_gn) < 1e-4 * max(1.0, ref_gn)
+        for k in ref_state:
+            assert torch.allclose(torch.as_tensor(state[k]), ref_state[k], rtol=1e-4, atol=1e-6), k
+    assert ref_losses[-1] < ref_losses[0] + 0.5   # sanity: not diverging
+
+
+def test_loss_decreases_single_process():
+    from midgpt_b200.train import Trainer
+    cfg = _tiny_cfg(False)
+    cfg.learning_rate, cfg.warmup_steps = 3e-3, 2
+    tr = Trainer(cfg, device_type="cpu")
+    x, y = _batches(cfg, 1)[0]
+    losses = [tr.train_step(x, y).item() for _ in range(12)]
+    assert losses[-1] < losses[1] - 0.3, losses
