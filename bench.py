@@ -1,0 +1,247 @@
+#!/usr/bin/env python
+"""Headline benchmark: training throughput (tokens/s) of the reference's 1.5B config (``openwebtext_xl``:
+L24 H16 D2048 T1024 V50304, bf16 compute / fp32 master, FSDP) — BASELINE.md, reference README.md:55.
+
+    python bench.py                                   # 1 GPU, defaults that finish in minutes
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29501 \
+        bench.py --gpus 8 --steps 10 --warmup 3       # one rank per GPU (what the driver runs)
+    python bench.py --impl reference                  # the unmodified reference (unavailable here: no jax)
+
+Weak scaling: every GPU processes ``--seqs-per-gpu`` (default 128) sequences of 1024 tokens per optimizer
+step, so N = 8 is exactly the reference's global batch of 1024 sequences.  Each step is a full training
+step: forward, backward, gradient reduction, global-norm clip, AdamW, bf16 re-gather.  Synthetic tokens,
+random-init weights (no network for datasets/checkpoints).
+
+Two numbers:
+  * ``value``  — device-timed (CUDA events, max over ranks) with batches already resident on the GPU;
+  * ``e2e``    — the same K steps through the public API (``PinnedBatchLoader`` → ``Trainer.train_step`` →
+                 ``loss.item()``): H2D copy of every batch from pinned memory and a D2H read of the loss
+                 inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PUBLISHED_TOKENS_PER_S = 444_000.0     # reference README.md:55 (TPU v3-128), BASELINE.md
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=4)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--config", default="openwebtext_xl")
+    p.add_argument("--backend", default="b200", choices=["b200", "torch"])
+    p.add_argument("--comm", default="auto")
+    p.add_argument("--seqs-per-gpu", type=int, default=128)
+    p.add_argument("--micro-bs", type=int, default=0)
+    p.add_argument("--remat", default="auto", choices=["auto", "block", "none"])
+    p.add_argument("--gather-mode", default="auto")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--set", action="append", default=[])
+    return p.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2]); power.append(float(r[3]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+def reference_arm():
+    """The reference needs jax/jaxlib/equinox/optax/orbax; none is installed or present in /opt/wheelhouse and the
+    repo has no setup.py/pyproject (pip: 'not installable'), see DESIGN.md §Reference arm."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    why = "reference is a Jax/Equinox script tree (no setup.py/pyproject; pip --no-index install fails) and jax/jaxlib/equinox/optax/orbax are not in the image or /opt/wheelhouse"
+    try:
+        import jax  # noqa: F401
+        why = "jax present but reference not installed under baseline/_ref" if not os.path.isdir(ref) else why
+    except Exception:
+        pass
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+
+    import torch
+    import torch.distributed as dist
+    from midgpt_b200 import load_config
+    from midgpt_b200.data import BatchSampler, PinnedBatchLoader, synthetic_tokens
+    from midgpt_b200.models.params import flops_per_token
+    from midgpt_b200.train import Trainer
+    from midgpt_b200.utils import obs
+    sys.path.insert(0, ROOT)
+    from launch import apply_overrides
+
+    cfg = load_config(args.config)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    cfg.batch_size = args.seqs_per_gpu * world
+    cfg.g_accum_iters = 1
+    cfg.engine.backend = args.backend
+    cfg.engine.comm = args.comm
+    cfg.engine.gather_mode = args.gather_mode
+    cfg.engine.micro_batch_size = args.micro_bs
+    apply_overrides(cfg, args.set)
+    T = cfg.model_config.block_size
+    if args.remat == "auto":
+        # full activation stash needs ~70 KB/token for the 1.5 B model; keep it when it fits comfortably in 180 GB
+        cfg.engine.remat = "none"
+    else:
+        cfg.engine.remat = args.remat
+
+    tr = Trainer(cfg, device_type="cuda")
+    m = tr.mesh
+    dev = m.device
+    n_resident = 4
+    gen = torch.Generator().manual_seed(1234 + m.rank)
+    V = cfg.model_config.vocab_size
+    resident = [(torch.randint(0, V, (tr.local_seqs, T), generator=gen, dtype=torch.int32).to(dev),
+                 torch.randint(0, V, (tr.local_seqs, T), generator=gen, dtype=torch.int32).to(dev)) for _ in range(n_resident)]
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ------------------------------------------------------------------ warm-up (also compiles nothing: no JIT)
+    for i in range(args.warmup):
+        x, y = resident[i % n_resident]
+        loss = tr.train_step(x, y)
+    sync()
+    loss_w = loss.item() if args.warmup else float("nan")
+
+    # ------------------------------------------------------------------ device-timed region
+    clocks = ClockSampler(m.local_rank)
+    if m.is_main:
+        clocks.start()
+    launches0 = getattr(tr.backend, "launches", 0)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        x, y = resident[(args.warmup + i) % n_resident]
+        loss = tr.train_step(x, y)
+    e1.record()
+    sync()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = getattr(tr.backend, "launches", 0) - launches0
+    clk = clocks.stop() if m.is_main else {}
+    ms_per_step = ms_total / args.steps
+    tokens_per_step = tr.tokens_per_step
+    value = tokens_per_step / (ms_per_step * 1e-3)
+    final_loss = loss.item()
+
+    # ------------------------------------------------------------------ end-to-end region (public API, H2D + D2H every step)
+    e2e = None
+    if not args.no_e2e:
+        corpus = synthetic_tokens(max(8 * T * tr.local_seqs, 1 << 22), V, seed=7 + m.rank)
+        loader = PinnedBatchLoader(BatchSampler(corpus, T, seed=11 + m.rank), tr.local_seqs, dev)
+        x, y = loader.next()
+        tr.train_step(x, y).item()                      # one untimed step to prime the loader pipeline
+        sync()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            x, y = loader.next()                        # pinned host -> device copy of this step's batch
+            lv = tr.train_step(x, y).item()             # device -> host read of this step's loss
+        sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        loader.close()
+        e2e = {"value": tokens_per_step * args.steps / dt, "unit": "tokens/s",
+               "h2d_bytes_per_step": loader.h2d_bytes_per_batch * world, "d2h_bytes_per_step": 4 * world,
+               "ms_per_step": dt / args.steps * 1e3, "last_loss": lv}
+
+    if m.is_main:
+        peak, how = obs.peak_flops_per_gpu()
+        fpt = flops_per_token(cfg.model_config)
+        out = {
+            "metric": "training throughput, 1.5B openwebtext_xl (tokens/s)" if args.config == "openwebtext_xl" else f"training throughput, {args.config} (tokens/s)",
+            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / PUBLISHED_TOKENS_PER_S if args.config == "openwebtext_xl" else None,
+            "dtype": "bf16", "data": "synthetic tokens, random-init weights",
+            "impl": "ours",
+            "mfu_nominal_2.25PF": value * fpt / (2.25e15 * world),
+            f"mfu_{how}_cublas_peak": value * fpt / (peak * world),
+            "config": {"model": f"{args.config} L{cfg.model_config.n_layer} H{cfg.model_config.n_head} D{cfg.model_config.n_embd} T{T} V{V}",
+                       "global_batch": cfg.batch_size, "seq_len": T,
+                       "parallelism": (f"fsdp{m.shard_size}" if m.shard_size > 1 else "single") + (f"xdp{m.replica_size}" if m.replica_size > 1 else ""),
+                       "micro_batch": tr.micro_bs, "n_micro": tr.n_micro, "remat": cfg.engine.remat, "backend": tr.backend.name,
+                       "comm": tr.engine.comm, "gather_mode": tr.engine.gather_mode,
+                       "l2": "no L2 flush needed: per-step working set (2.8 GB bf16 weights + GBs of activations, 4 rotating batches) >> 126 MB L2"},
+            "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons"),
+                       "power_w_max": clk.get("power_w_max")},
+            "e2e": e2e, "gpu_launches": launches, "loss_after_warmup": loss_w, "final_loss": final_loss,
+            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

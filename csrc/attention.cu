@@ -1,0 +1,638 @@
+// Causal flash attention for sm_100a on tcgen05 / TMEM / TMA — forward and backward.
+//
+// Inputs are the already QK-LayerNorm'ed + RoPE'd q, k and the raw v, as [B, T, H, C] views with an
+// arbitrary token stride (so q/k come from the packed [M, 2D] buffer and v straight from the
+// projection output — no copies).  Scores are scaled by 1/sqrt(C) inside an fp32 softmax
+// (reference src/model.py:71-77).  C ∈ {64, 128}.
+//
+// Forward  (one CTA = one (batch, head, 128-query tile); 2 CTAs co-reside per SM and fill each other's bubbles)
+//   warps 0-3  softmax: thread = one query row; S row read from TMEM, online max/sum with lazy (threshold)
+//              rescaling of the O accumulator *in TMEM*, P written as bf16 into 128B-swizzled smem
+//   warp 4     TMA producer (Q once, K/V double buffered)
+//   warp 5     tcgen05.mma issuer:  S = Q·Kᵀ (SS, fp32 in TMEM),  O += P·V (P K-major smem, V MN-major smem)
+// Backward (one CTA = one (batch, head, 128-key tile), loops over the query tiles at or below the diagonal)
+//   S = Q·Kᵀ, dP = dO·Vᵀ  →  P = exp2(S·c − lse), dS = P∘(dP − δ)/√C  →  dV += Pᵀ·dO, dK += dSᵀ·Q (TMEM-resident
+//   accumulators), dQ = dS·K is produced per tile in TMEM (aliasing S) and reduced into an fp32 buffer with
+//   vector atomics.  Every operand tile is loaded once and used through both K-major and MN-major descriptors.
+#include "common.cuh"
+
+#include <stdexcept>
+#include <string>
+
+namespace mg {
+
+typedef CUresult (*PFN_encodeTiled4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static CUtensorMap make_tmap_bthc(const void* ptr, int B, int T, int H, int C, long long row_stride, int box_rows) {
+  static PFN_encodeTiled4 fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      throw std::runtime_error("cuTensorMapEncodeTiled entry point not found");
+    fn = reinterpret_cast<PFN_encodeTiled4>(p);
+  }
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)row_stride * 2, (cuuint64_t)row_stride * 2 * T};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("attention: cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return m;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// Write 8 bf16 (one 16-byte chunk) of row r, logical column chunk cc (8-element units) into a K-major,
+// 128B-swizzled tile made of 64-column blocks of `rows` rows each.
+MG_DEVICE void st_swizzled_chunk(uint8_t* tile, int rows, int r, int cc, uint4 v) {
+  const int blk = cc >> 3, c = cc & 7;
+  *reinterpret_cast<uint4*>(tile + blk * (rows * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+}
+
+// ================================================================================================
+// Forward
+// ================================================================================================
+template <int C>
+struct FwdCfg {
+  static constexpr int BQ = 128;
+  static constexpr int BKV = (C == 64) ? 128 : 64;
+  static constexpr int Q_BYTES = BQ * C * 2;
+  static constexpr int K_BYTES = BKV * C * 2;
+  static constexpr int V_BYTES = BKV * C * 2;
+  static constexpr int P_BYTES = BQ * BKV * 2;
+  static constexpr int SMEM = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int S_COL = 0, O_COL = BKV;
+};
+
+template <int C>
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
+                int T, int H, float scale) {
+  using Cfg = FwdCfg<C>;
+  constexpr int BQ = Cfg::BQ, BKV = Cfg::BKV;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + 2 * Cfg::K_BYTES;
+  uint8_t* sP = sV + 2 * Cfg::V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 1
+  uint64_t* p_full = bars + 10;       // 1 (128 arrivals)
+  uint64_t* pv_done = bars + 11;      // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;          // heavy (late) query tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * BQ;
+  const int n_kv = min((q0 + BQ + BKV - 1) / BKV, (T + BKV - 1) / BKV);   // causal: keys < q0 + BQ
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sQ + cb * (BQ * 128), &tmQ, q_full, cb * 64, h, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::K_BYTES);
+#pragma unroll
+        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sK + st * Cfg::K_BYTES + cb * (BKV * 128), &tmK, &k_full[st], cb * 64, h, j * BKV, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], Cfg::V_BYTES);
+#pragma unroll
+        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sV + st * Cfg::V_BYTES + cb * (BKV * 128), &tmV, &v_full[st], cb * 64, h, j * BKV, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, C, 0, 1);
+      const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_base = smem_u32(sK + st * Cfg::K_BYTES);
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k) {
+          const uint32_t blk = (k * 16) / 64, in = (k * 16) % 64;
+          umma_bf16_ss(tmem + Cfg::S_COL, make_smem_desc(q_base + blk * (BQ * 128) + in * 2, 16, 1024),
+                       make_smem_desc(k_base + blk * (BKV * 128) + in * 2, 16, 1024), idesc_s, k != 0);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(p_full, j & 1);          // P_j is in smem and S_j has been fully read
+        tc_fence_after();
+        if (j + 1 < n_kv) issue_qk(j + 1);
+        const int st = j & 1;
+        mbar_wait(&v_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t v_base = smem_u32(sV + st * Cfg::V_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint32_t blk = (k * 16) / 64, in = (k * 16) % 64;
+          umma_bf16_ss(tmem + Cfg::O_COL, make_smem_desc(p_base + blk * (BQ * 128) + in * 2, 16, 1024),
+                       make_smem_desc(v_base + k * 2048, BKV * 128, 1024), idesc_o, (j | k) != 0);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ------------------------------- softmax warps (thread = query row) -------------------------------
+    const int row = threadIdx.x;                 // 0..127, also the TMEM lane
+    const int q_idx = q0 + row;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const float sl2 = scale * kLog2e;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kv0 = j * BKV;
+      const bool need_mask = (kv0 + BKV - 1 > q0);          // tile touches or crosses the diagonal
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ch = 0; ch < BKV / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float v = __uint_as_float(r[e]) * sl2;
+          if (need_mask && (kv0 + ch * 32 + e > q_idx)) v = -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);           // O_{j-1} complete; P buffer free
+        tc_fence_after();
+        const bool need = mx > m_used + 8.f;       // lazy rescale: only when the max grew by > 2^8
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m_used - mx) : 1.f;
+          if (need) m_used = mx;
+          l *= alpha;
+#pragma unroll
+          for (int ch = 0; ch < C / 16; ++ch) {
+            uint32_t r[16];
+            tmem_ld_x16(t_lane + Cfg::O_COL + ch * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+            tmem_st_x16(t_lane + Cfg::O_COL + ch * 16, r);
+          }
+          tmem_st_wait();
+        }
+      } else {
+        m_used = mx;
+      }
+      // pass 2: P = exp2(s - m_used) -> bf16 -> swizzled smem (K-major A operand of P·V)
+#pragma unroll
+      for (int ch = 0; ch < BKV / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float v = __uint_as_float(r[e]) * sl2 - m_used;
+          float pe = exp2f(v);
+          if (need_mask && (kv0 + ch * 32 + e > q_idx)) pe = 0.f;
+          p[e] = pe;
+          l += pe;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v4 = make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
+                                pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7]));
+          st_swizzled_chunk(sP, BQ, row, ch * 4 + g, v4);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> bf16 -> global ; lse
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const bool valid = q_idx < T;
+    __nv_bfloat16* orow = out + ((static_cast<long long>(b) * T + q_idx) * H + h) * C;
+#pragma unroll
+    for (int ch = 0; ch < C / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld_x32(t_lane + Cfg::O_COL + ch * 32, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v4;
+          v4.x = pack_bf16(__uint_as_float(r[8 * g]) * inv_l, __uint_as_float(r[8 * g + 1]) * inv_l);
+          v4.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * inv_l, __uint_as_float(r[8 * g + 3]) * inv_l);
+          v4.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * inv_l, __uint_as_float(r[8 * g + 5]) * inv_l);
+          v4.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * inv_l, __uint_as_float(r[8 * g + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + ch * 32 + g * 8) = v4;
+        }
+      }
+    }
+    if (valid) lse_out[(static_cast<long long>(b) * H + h) * T + q_idx] = (m_used + log2f(l)) * kLn2;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ================================================================================================
+// Backward
+// ================================================================================================
+// delta[b,h,t] = sum_c dO·O  (one warp per (token, head))
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                            float* __restrict__ delta, int B, int T, int H, int C) {
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= static_cast<long long>(B) * T * H) return;
+  const int hh = w % H;
+  const long long bt = w / H;
+  const __nv_bfloat16* po = o + w * C;
+  const __nv_bfloat16* pd = dout + w * C;
+  float acc = 0.f;
+  for (int c = lane * 2; c < C; c += 64) {
+    float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(po + c));
+    float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(pd + c));
+    acc += a.x * d.x + a.y * d.y;
+  }
+  acc = warp_sum(acc);
+  const long long bb = bt / T, t = bt % T;
+  if (lane == 0) delta[(bb * H + hh) * T + t] = acc;
+}
+
+// dq (bf16, strided) = dq_accum (fp32 [M, D])
+__global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long M, int D, long long ld) {
+  const int nv = D >> 2;
+  const long long total = M * nv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / nv;
+    const int j = i - m * nv;
+    float4 v = __ldg(reinterpret_cast<const float4*>(acc + m * D) + j);
+    *reinterpret_cast<uint2*>(dq + m * ld + j * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+template <int C>
+struct BwdCfg {
+  static constexpr int BQ = 128, BKV = 128;
+  static constexpr int TILE = 128 * C * 2;             // one [128 x C] bf16 operand tile
+  static constexpr int PS = 128 * 128 * 2;             // P / dS tiles
+  static constexpr int SMEM = 4 * TILE + 2 * PS + 256 + 1024;   // K, V, Q, dO, P, dS
+  static constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + C;   // dQ aliases S
+  static constexpr int TMEM_COLS = 512;
+};
+
+template <int C>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_accum,
+                __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long dkv_row_stride, int T, int H,
+                float scale) {
+  using Cfg = BwdCfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + Cfg::TILE;
+  uint8_t* sQ = sV + Cfg::TILE;
+  uint8_t* sdO = sQ + Cfg::TILE;
+  uint8_t* sP = sdO + Cfg::TILE;
+  uint8_t* sdS = sP + Cfg::PS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + Cfg::PS);
+  uint64_t* kv_full = bars;        // K and V landed
+  uint64_t* q_full = bars + 1;     // Q_i landed
+  uint64_t* do_full = bars + 2;    // dO_i landed
+  uint64_t* qdo_empty = bars + 3;  // Q_i / dO_i no longer read by any MMA
+  uint64_t* s_full = bars + 4;     // S ready
+  uint64_t* dp_full = bars + 5;    // dP ready
+  uint64_t* p_ready = bars + 6;    // P in smem (128 arrivals)
+  uint64_t* ds_ready = bars + 7;   // dS in smem, S/dP fully read (128 arrivals)
+  uint64_t* dq_full = bars + 8;    // dQ tile complete in TMEM (and dV/dK MMAs of this tile retired)
+  uint64_t* dq_drained = bars + 9; // dQ read out (128 arrivals) -> S columns reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x;                     // key tile (small index = most work, scheduled first)
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kv0 = jt * 128;
+  const int nq = (T + 127) / 128;
+  const int n_it = nq - jt;                      // query tiles jt .. nq-1
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(qdo_empty, 1);
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 128); mbar_init(ds_ready, 128);
+    mbar_init(dq_full, 1); mbar_init(dq_drained, 128);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * Cfg::TILE);
+#pragma unroll
+      for (int cb = 0; cb < C / 64; ++cb) {
+        tma_load_4d(sK + cb * (128 * 128), &tmK, kv_full, cb * 64, h, kv0, b);
+        tma_load_4d(sV + cb * (128 * 128), &tmV, kv_full, cb * 64, h, kv0, b);
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int q0 = (jt + it) * 128;
+        mbar_wait(qdo_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, Cfg::TILE);
+#pragma unroll
+        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sQ + cb * (128 * 128), &tmQ, q_full, cb * 64, h, q0, b);
+        mbar_expect_tx(do_full, Cfg::TILE);
+#pragma unroll
+        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sdO + cb * (128 * 128), &tmdO, do_full, cb * 64, h, q0, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP : both operands K-major, N = 128
+      constexpr uint32_t idesc_mm = make_idesc_bf16(128, C, 1, 1);     // dV, dK: both MN-major, N = C
+      constexpr uint32_t idesc_km = make_idesc_bf16(128, C, 0, 1);     // dQ    : A K-major (dS), B MN-major (K)
+      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), q_base = smem_u32(sQ), do_base = smem_u32(sdO);
+      const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sdS);
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const uint32_t ph = it & 1;
+        if (it > 0) { mbar_wait(dq_drained, (it - 1) & 1); }
+        mbar_wait(q_full, ph);
+        tc_fence_after();
+        // S = Q · Kᵀ
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k) {
+          const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
+          umma_bf16_ss(tmem + Cfg::S_COL, make_smem_desc(q_base + off, 16, 1024), make_smem_desc(k_base + off, 16, 1024), idesc_kk, k != 0);
+        }
+        umma_commit(s_full);
+        mbar_wait(do_full, ph);
+        tc_fence_after();
+        // dP = dO · Vᵀ
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k) {
+          const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
+          umma_bf16_ss(tmem + Cfg::DP_COL, make_smem_desc(do_base + off, 16, 1024), make_smem_desc(v_base + off, 16, 1024), idesc_kk, k != 0);
+        }
+        umma_commit(dp_full);
+        // dV += Pᵀ · dO        (A = P as MN-major [k = q rows][m = kv], B = dO as MN-major [k = q rows][n = c])
+        mbar_wait(p_ready, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_bf16_ss(tmem + Cfg::DV_COL, make_smem_desc(p_base + k * 2048, 128 * 128, 1024),
+                       make_smem_desc(do_base + k * 2048, 128 * 128, 1024), idesc_mm, (it | k) != 0);
+        // dK += dSᵀ · Q ; dQ = dS · K
+        mbar_wait(ds_ready, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_bf16_ss(tmem + Cfg::DK_COL, make_smem_desc(ds_base + k * 2048, 128 * 128, 1024),
+                       make_smem_desc(q_base + k * 2048, 128 * 128, 1024), idesc_mm, (it | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k) {
+          const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
+          umma_bf16_ss(tmem + Cfg::S_COL, make_smem_desc(ds_base + off, 16, 1024), make_smem_desc(k_base + k * 2048, 128 * 128, 1024), idesc_km, k != 0);
+        }
+        umma_commit(qdo_empty);
+        umma_commit(dq_full);
+      }
+    }
+  } else {
+    // thread = query row inside the current query tile (and kv row in the final dK/dV epilogue)
+    const int row = threadIdx.x;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const float sl2 = scale * kLog2e;
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = it & 1;
+      const int q0 = (jt + it) * 128;
+      const int q_idx = q0 + row;
+      const bool qvalid = q_idx < T;
+      const long long sidx = (static_cast<long long>(b) * H + h) * T + q_idx;
+      const float lse2 = qvalid ? lse[sidx] * kLog2e : 0.f;
+      const float dlt = qvalid ? delta[sidx] : 0.f;
+      const bool diag = (it == 0);
+      if (it > 0) {
+        // P and dS buffers are free once the previous tile's dV/dK/dQ MMAs retired (dq_full) — waited below before reuse
+      }
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // P = exp2(S*c - lse) -> smem
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int kv = kv0 + ch * 32 + e;
+          float pe = exp2f(__uint_as_float(r[e]) * sl2 - lse2);
+          if (!qvalid || kv >= T || (diag && kv > q_idx)) pe = 0.f;
+          p[e] = pe;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v4 = make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
+                                pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7]));
+          st_swizzled_chunk(sP, 128, row, ch * 4 + g, v4);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(p_ready);
+      // dS = P ∘ (dP − δ) · scale -> smem   (P recomputed from S, which is still in TMEM)
+      mbar_wait(dp_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32], d[32];
+        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+        tmem_ld_x32(t_lane + Cfg::DP_COL + ch * 32, d);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int kv = kv0 + ch * 32 + e;
+          float pe = exp2f(__uint_as_float(r[e]) * sl2 - lse2);
+          if (!qvalid || kv >= T || (diag && kv > q_idx)) pe = 0.f;
+          ds[e] = pe * (__uint_as_float(d[e]) - dlt) * scale;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v4 = make_uint4(pack_bf16(ds[8 * g], ds[8 * g + 1]), pack_bf16(ds[8 * g + 2], ds[8 * g + 3]),
+                                pack_bf16(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16(ds[8 * g + 6], ds[8 * g + 7]));
+          st_swizzled_chunk(sdS, 128, row, ch * 4 + g, v4);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(ds_ready);
+      // drain dQ (aliases S): fp32 vector atomics into dq_accum
+      mbar_wait(dq_full, ph);
+      tc_fence_after();
+      float* dqrow = dq_accum + ((static_cast<long long>(b) * T + q_idx) * H + h) * C;
+#pragma unroll
+      for (int ch = 0; ch < C / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+        tmem_ld_wait();
+        if (qvalid) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            atomicAdd(reinterpret_cast<float4*>(dqrow + ch * 32 + g * 4),
+                      make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                                  __uint_as_float(r[4 * g + 3])));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_drained);
+    }
+    // epilogue: dV, dK (thread = kv row).  The last dq_full wait above also covers the final dV/dK MMAs.
+    const int kv_idx = kv0 + row;
+    const bool kvalid = kv_idx < T;
+    const long long krow = kvalid ? (static_cast<long long>(b) * T + kv_idx) : 0;
+    __nv_bfloat16* dvrow = dv + krow * dkv_row_stride + static_cast<long long>(h) * C;
+    __nv_bfloat16* dkrow = dk + krow * dkv_row_stride + static_cast<long long>(h) * C;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* dst = which ? dkrow : dvrow;
+      const uint32_t col = which ? Cfg::DK_COL : Cfg::DV_COL;
+#pragma unroll
+      for (int ch = 0; ch < C / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(t_lane + col + ch * 32, r);     // warp-collective: executed by every lane, stores are guarded
+        tmem_ld_wait();
+        if (kvalid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v4;
+            v4.x = pack_bf16(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
+            v4.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+            v4.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+            v4.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+            *reinterpret_cast<uint4*>(dst + ch * 32 + g * 8) = v4;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+template <typename K>
+static void set_smem(K kern, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(attention): ") + cudaGetErrorString(e));
+}
+static void check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, int C, long long q_row_stride,
+              long long k_row_stride, long long v_row_stride, int num_sms, cudaStream_t s) {
+  const float scale = 1.f / sqrtf(static_cast<float>(C));
+  dim3 grid((T + 127) / 128, H, B);
+  if (C == 64) {
+    using Cfg = FwdCfg<64>;
+    CUtensorMap tq = make_tmap_bthc(q, B, T, H, C, q_row_stride, Cfg::BQ), tk = make_tmap_bthc(k, B, T, H, C, k_row_stride, Cfg::BKV),
+                tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, Cfg::BKV);
+    static bool once = (set_smem(attn_fwd_kernel<64>, Cfg::SMEM), true);
+    (void)once;
+    attn_fwd_kernel<64><<<grid, 192, Cfg::SMEM, s>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, T, H, scale);
+  } else if (C == 128) {
+    using Cfg = FwdCfg<128>;
+    CUtensorMap tq = make_tmap_bthc(q, B, T, H, C, q_row_stride, Cfg::BQ), tk = make_tmap_bthc(k, B, T, H, C, k_row_stride, Cfg::BKV),
+                tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, Cfg::BKV);
+    static bool once = (set_smem(attn_fwd_kernel<128>, Cfg::SMEM), true);
+    (void)once;
+    attn_fwd_kernel<128><<<grid, 192, Cfg::SMEM, s>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, T, H, scale);
+  } else {
+    throw std::runtime_error("attention: head_dim must be 64 or 128");
+  }
+  check("attn_fwd");
+}
+
+void attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* delta, void* dq,
+              void* dk, void* dv, float* dq_accum, int B, int T, int H, int C, long long q_row_stride, long long k_row_stride,
+              long long v_row_stride, long long dqkv_row_stride, int num_sms, cudaStream_t s) {
+  const float scale = 1.f / sqrtf(static_cast<float>(C));
+  const long long nwarp = static_cast<long long>(B) * T * H;
+  attn_bwd_prep_kernel<<<static_cast<unsigned>((nwarp + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, B, T, H, C);
+  check("attn_bwd_prep");
+  dim3 grid((T + 127) / 128, H, B);
+  CUtensorMap tq = make_tmap_bthc(q, B, T, H, C, q_row_stride, 128), tk = make_tmap_bthc(k, B, T, H, C, k_row_stride, 128),
+              tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, 128), tdo = make_tmap_bthc(dout, B, T, H, C, static_cast<long long>(H) * C, 128);
+  if (C == 64) {
+    static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
+    (void)once;
+    attn_bwd_kernel<64><<<grid, 192, BwdCfg<64>::SMEM, s>>>(tq, tk, tv, tdo, lse, delta, dq_accum, static_cast<__nv_bfloat16*>(dk),
+                                                             static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale);
+  } else if (C == 128) {
+    static bool once = (set_smem(attn_bwd_kernel<128>, BwdCfg<128>::SMEM), true);
+    (void)once;
+    attn_bwd_kernel<128><<<grid, 192, BwdCfg<128>::SMEM, s>>>(tq, tk, tv, tdo, lse, delta, dq_accum, static_cast<__nv_bfloat16*>(dk),
+                                                               static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale);
+  } else {
+    throw std::runtime_error("attention: head_dim must be 64 or 128");
+  }
+  check("attn_bwd");
+  dq_convert_kernel<<<num_sms * 8, 256, 0, s>>>(dq_accum, static_cast<__nv_bfloat16*>(dq), static_cast<long long>(B) * T, H * C, dqkv_row_stride);
+  check("dq_convert");
+}
+
+}  // namespace mg

@@ -1,0 +1,219 @@
+// Python bindings (torch extension).  Thin: argument checking + stream lookup; kernels live in the .cu files.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+
+namespace mg {
+void gemm_launch(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d, long long ldd,
+                 void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int accumulate,
+                 int num_sms, cudaStream_t stream);
+void rmsnorm_fwd(const void* x, void* y, float* rstd, int M, int D, float eps, cudaStream_t s);
+void rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* dres, void* dx, int M, int D, cudaStream_t s);
+void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const float* sin_t, const float* cos_t, void* qk,
+                   float* stats, long long M, int T, int H, int C, float eps, cudaStream_t s);
+void qkln_rope_bwd(void* dqkv, const void* qkv_raw, const float* stats, const float* qg, const float* kg, const float* sin_t,
+                   const float* cos_t, float* dqg, float* dkg, long long M, int T, int H, int C, int num_sms, cudaStream_t s);
+void embed_fwd(const void* wte, const int* idx, void* out, long long M, int D, int num_sms, cudaStream_t s);
+void embed_bwd(const void* dx, const int* idx, float* dwte, long long M, int D, int num_sms, cudaStream_t s);
+void ce_chunk(void* logits, long long ldl, const int* targets, float* loss_sum, int rows, int V, float grad_scale,
+              int write_grad, cudaStream_t s);
+void dropout(const void* x, void* y, long long n, float p, unsigned long long seed, int num_sms, cudaStream_t s);
+void sumsq_accumulate(const float* g, long long n, float* out, int num_sms, cudaStream_t s);
+void adamw_step(float* p, float* m, float* v, float* g, void* p_lp, long long n, const float* clip_ptr, float lr, float b1,
+                float b2, float eps, float wd_over_lr_peak, float bc1, float bc2, int zero_grad, int num_sms, cudaStream_t s);
+void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, int C, long long q_row_stride,
+              long long kv_row_stride_k, long long kv_row_stride_v, int num_sms, cudaStream_t s);
+void attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* delta,
+              void* dq, void* dk, void* dv, float* dq_accum, int B, int T, int H, int C, long long q_row_stride,
+              long long k_row_stride, long long v_row_stride, long long dqkv_row_stride, int num_sms, cudaStream_t s);
+}  // namespace mg
+
+namespace {
+
+int num_sms_of(const at::Tensor& t) {
+  static int cached[16] = {0};
+  const int dev = t.get_device();
+  if (!cached[dev]) cached[dev] = at::cuda::getDeviceProperties(dev)->multiProcessorCount;
+  return cached[dev];
+}
+cudaStream_t stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+#define CHECK_BF16(t) TORCH_CHECK((t).is_cuda() && (t).scalar_type() == at::kBFloat16, #t " must be a CUDA bf16 tensor")
+#define CHECK_F32(t) TORCH_CHECK((t).is_cuda() && (t).scalar_type() == at::kFloat, #t " must be a CUDA fp32 tensor")
+#define CHECK_2D_ROWMAJOR(t) TORCH_CHECK((t).dim() == 2 && (t).stride(1) == 1, #t " must be 2-D with unit inner stride")
+
+// d (+)= op(a) · op(b)ᵀ ; see csrc/gemm.cu for operand conventions.
+void gemm(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn, at::Tensor& d, int64_t epi,
+          const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& aux, bool accumulate) {
+  c10::cuda::CUDAGuard guard(a.device());
+  CHECK_BF16(a); CHECK_BF16(b); CHECK_2D_ROWMAJOR(a); CHECK_2D_ROWMAJOR(b); CHECK_2D_ROWMAJOR(d);
+  const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int64_t N = b_mn ? b.size(1) : b.size(0), Kb = b_mn ? b.size(0) : b.size(1);
+  TORCH_CHECK(K == Kb, "gemm: inner dimensions differ: ", K, " vs ", Kb);
+  TORCH_CHECK(d.size(0) == M && d.size(1) == N, "gemm: output must be [", M, ", ", N, "]");
+  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "gemm: leading dimensions must be multiples of 8 elements (16 B)");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) % 16 == 0) && (reinterpret_cast<uintptr_t>(b.data_ptr()) % 16 == 0) &&
+              (reinterpret_cast<uintptr_t>(d.data_ptr()) % 16 == 0), "gemm: base pointers must be 16-byte aligned");
+  if (epi == 4) { CHECK_F32(d); TORCH_CHECK(d.stride(0) % 4 == 0); }
+  else { CHECK_BF16(d); TORCH_CHECK(d.stride(0) % 8 == 0); }
+  const void* auxp = nullptr; long long ld_aux = 0;
+  if (epi == 1 || epi == 3) {
+    TORCH_CHECK(aux.has_value(), "gemm: this epilogue needs aux");
+    CHECK_BF16(*aux); CHECK_2D_ROWMAJOR(*aux);
+    TORCH_CHECK(aux->size(0) == M && aux->size(1) == N && N % 64 == 0 && aux->stride(0) % 8 == 0);
+    auxp = aux->data_ptr(); ld_aux = aux->stride(0);
+  }
+  void* d2p = nullptr; long long ldd2 = 0;
+  if (epi == 2) {
+    TORCH_CHECK(d2.has_value(), "gemm: GELU epilogue needs d2");
+    CHECK_BF16(*d2); CHECK_2D_ROWMAJOR(*d2);
+    TORCH_CHECK(d2->size(0) == M && d2->size(1) == N);
+    d2p = d2->data_ptr(); ldd2 = d2->stride(0);
+  }
+  mg::gemm_launch(a.data_ptr(), a.stride(0), a_mn, b.data_ptr(), b.stride(0), b_mn, d.data_ptr(), d.stride(0), d2p, ldd2, auxp,
+                  ld_aux, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), accumulate ? 1 : 0,
+                  num_sms_of(a), stream());
+}
+
+std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, double eps) {
+  c10::cuda::CUDAGuard guard(x.device());
+  CHECK_BF16(x); TORCH_CHECK(x.dim() == 2 && x.is_contiguous());
+  auto y = at::empty_like(x);
+  auto rstd = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  mg::rmsnorm_fwd(x.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), x.size(0), x.size(1), static_cast<float>(eps), stream());
+  return {y, rstd};
+}
+at::Tensor rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& rstd, const c10::optional<at::Tensor>& dres) {
+  c10::cuda::CUDAGuard guard(x.device());
+  CHECK_BF16(dy); CHECK_BF16(x); CHECK_F32(rstd);
+  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && dy.sizes() == x.sizes());
+  if (dres.has_value()) { CHECK_BF16(*dres); TORCH_CHECK(dres->is_contiguous() && dres->sizes() == x.sizes()); }
+  auto dx = at::empty_like(x);
+  mg::rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), rstd.data_ptr<float>(), dres.has_value() ? dres->data_ptr() : nullptr, dx.data_ptr(),
+                  x.size(0), x.size(1), stream());
+  return dx;
+}
+
+std::vector<at::Tensor> qkln_rope_fwd(const at::Tensor& qkv, const at::Tensor& qg, const at::Tensor& kg, const at::Tensor& sin_t,
+                                      const at::Tensor& cos_t, int64_t T, int64_t H, int64_t C, double eps) {
+  c10::cuda::CUDAGuard guard(qkv.device());
+  CHECK_BF16(qkv); CHECK_F32(qg); CHECK_F32(kg); CHECK_F32(sin_t); CHECK_F32(cos_t);
+  TORCH_CHECK(qkv.is_contiguous() && qkv.dim() == 2 && qkv.size(1) == 3 * H * C);
+  TORCH_CHECK(sin_t.is_contiguous() && sin_t.size(0) >= T && sin_t.size(1) == C / 2);
+  const int64_t M = qkv.size(0);
+  auto qk = at::empty({M, 2 * H * C}, qkv.options());
+  auto stats = at::empty({M, 2, H, 2}, qkv.options().dtype(at::kFloat));
+  mg::qkln_rope_fwd(qkv.data_ptr(), qg.data_ptr<float>(), kg.data_ptr<float>(), sin_t.data_ptr<float>(), cos_t.data_ptr<float>(),
+                    qk.data_ptr(), stats.data_ptr<float>(), M, T, H, C, static_cast<float>(eps), stream());
+  return {qk, stats};
+}
+void qkln_rope_bwd(at::Tensor& dqkv, const at::Tensor& qkv_raw, const at::Tensor& stats, const at::Tensor& qg, const at::Tensor& kg,
+                   const at::Tensor& sin_t, const at::Tensor& cos_t, at::Tensor& dqg, at::Tensor& dkg, int64_t T, int64_t H, int64_t C) {
+  c10::cuda::CUDAGuard guard(dqkv.device());
+  CHECK_BF16(dqkv); CHECK_BF16(qkv_raw); CHECK_F32(stats); CHECK_F32(qg); CHECK_F32(kg); CHECK_F32(dqg); CHECK_F32(dkg);
+  TORCH_CHECK(dqkv.is_contiguous() && qkv_raw.is_contiguous() && dqkv.sizes() == qkv_raw.sizes());
+  mg::qkln_rope_bwd(dqkv.data_ptr(), qkv_raw.data_ptr(), stats.data_ptr<float>(), qg.data_ptr<float>(), kg.data_ptr<float>(),
+                    sin_t.data_ptr<float>(), cos_t.data_ptr<float>(), dqg.data_ptr<float>(), dkg.data_ptr<float>(), dqkv.size(0), T, H, C,
+                    num_sms_of(dqkv), stream());
+}
+
+at::Tensor embed_fwd(const at::Tensor& wte, const at::Tensor& idx) {
+  c10::cuda::CUDAGuard guard(wte.device());
+  CHECK_BF16(wte); TORCH_CHECK(idx.is_cuda() && idx.scalar_type() == at::kInt && idx.is_contiguous());
+  TORCH_CHECK(wte.is_contiguous() && wte.size(1) % 8 == 0);
+  auto out = at::empty({idx.numel(), wte.size(1)}, wte.options());
+  mg::embed_fwd(wte.data_ptr(), idx.data_ptr<int>(), out.data_ptr(), idx.numel(), wte.size(1), num_sms_of(wte), stream());
+  return out;
+}
+void embed_bwd(const at::Tensor& dx, const at::Tensor& idx, at::Tensor& dwte) {
+  c10::cuda::CUDAGuard guard(dx.device());
+  CHECK_BF16(dx); CHECK_F32(dwte); TORCH_CHECK(idx.scalar_type() == at::kInt && idx.is_contiguous() && dx.is_contiguous() && dwte.is_contiguous());
+  mg::embed_bwd(dx.data_ptr(), idx.data_ptr<int>(), dwte.data_ptr<float>(), idx.numel(), dx.size(1), num_sms_of(dx), stream());
+}
+
+void ce_chunk(at::Tensor& logits, const at::Tensor& targets, at::Tensor& loss_sum, int64_t V, double grad_scale, bool write_grad) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  CHECK_BF16(logits); CHECK_F32(loss_sum); CHECK_2D_ROWMAJOR(logits);
+  TORCH_CHECK(targets.scalar_type() == at::kInt && targets.is_contiguous() && targets.numel() == logits.size(0));
+  TORCH_CHECK(logits.stride(0) % 8 == 0 && V <= logits.size(1));
+  mg::ce_chunk(logits.data_ptr(), logits.stride(0), targets.data_ptr<int>(), loss_sum.data_ptr<float>(), logits.size(0), V,
+               static_cast<float>(grad_scale), write_grad ? 1 : 0, stream());
+}
+
+at::Tensor dropout(const at::Tensor& x, double p, int64_t seed) {
+  c10::cuda::CUDAGuard guard(x.device());
+  CHECK_BF16(x); TORCH_CHECK(x.is_contiguous());
+  auto y = at::empty_like(x);
+  mg::dropout(x.data_ptr(), y.data_ptr(), x.numel(), static_cast<float>(p), static_cast<unsigned long long>(seed), num_sms_of(x), stream());
+  return y;
+}
+
+void sumsq_accumulate(const at::Tensor& g, at::Tensor& out) {
+  c10::cuda::CUDAGuard guard(g.device());
+  CHECK_F32(g); CHECK_F32(out); TORCH_CHECK(g.is_contiguous());
+  mg::sumsq_accumulate(g.data_ptr<float>(), g.numel(), out.data_ptr<float>(), num_sms_of(g), stream());
+}
+
+void adamw_step(at::Tensor& p, at::Tensor& m, at::Tensor& v, at::Tensor& g, const c10::optional<at::Tensor>& p_lp, const at::Tensor& clip,
+                double lr, double b1, double b2, double eps, double wd_over_lr_peak, double bc1, double bc2, bool zero_grad) {
+  c10::cuda::CUDAGuard guard(p.device());
+  CHECK_F32(p); CHECK_F32(m); CHECK_F32(v); CHECK_F32(g); CHECK_F32(clip);
+  TORCH_CHECK(p.is_contiguous() && m.is_contiguous() && v.is_contiguous() && g.is_contiguous());
+  TORCH_CHECK(p.numel() == m.numel() && p.numel() == v.numel() && p.numel() == g.numel());
+  void* lp = nullptr;
+  if (p_lp.has_value()) { CHECK_BF16(*p_lp); TORCH_CHECK(p_lp->is_contiguous() && p_lp->numel() == p.numel()); lp = p_lp->data_ptr(); }
+  mg::adamw_step(p.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), g.data_ptr<float>(), lp, p.numel(), clip.data_ptr<float>(),
+                 static_cast<float>(lr), static_cast<float>(b1), static_cast<float>(b2), static_cast<float>(eps),
+                 static_cast<float>(wd_over_lr_peak), static_cast<float>(bc1), static_cast<float>(bc2), zero_grad ? 1 : 0, num_sms_of(p), stream());
+}
+
+// q,k: [B,T,H,C] views with arbitrary row (token) stride; v likewise; returns (o [B*T, H*C], lse [B,H,T]).
+std::vector<at::Tensor> attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v) {
+  c10::cuda::CUDAGuard guard(q.device());
+  CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v);
+  TORCH_CHECK(q.dim() == 4 && q.stride(3) == 1 && q.stride(2) == q.size(3), "q must be [B,T,H,C] with packed heads");
+  TORCH_CHECK(k.stride(3) == 1 && k.stride(2) == k.size(3) && v.stride(3) == 1 && v.stride(2) == v.size(3));
+  const int64_t B = q.size(0), T = q.size(1), H = q.size(2), C = q.size(3);
+  TORCH_CHECK(q.stride(0) == T * q.stride(1) && k.stride(0) == T * k.stride(1) && v.stride(0) == T * v.stride(1));
+  auto o = at::empty({B * T, H * C}, q.options());
+  auto lse = at::empty({B, H, T}, q.options().dtype(at::kFloat));
+  mg::attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), B, T, H, C, q.stride(1), k.stride(1),
+               v.stride(1), num_sms_of(q), stream());
+  return {o, lse};
+}
+
+// dqkv: [B*T, 3*H*C] bf16 output (dq | dk | dv thirds).
+at::Tensor attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& o, const at::Tensor& dout,
+                    const at::Tensor& lse) {
+  c10::cuda::CUDAGuard guard(q.device());
+  CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(o); CHECK_BF16(dout); CHECK_F32(lse);
+  const int64_t B = q.size(0), T = q.size(1), H = q.size(2), C = q.size(3);
+  TORCH_CHECK(o.is_contiguous() && dout.is_contiguous());
+  auto dqkv = at::empty({B * T, 3 * H * C}, q.options());
+  auto delta = at::empty({B, H, T}, lse.options());
+  auto dq_accum = at::zeros({B * T, H * C}, lse.options());
+  char* base = static_cast<char*>(dqkv.data_ptr());
+  mg::attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(),
+               base, base + H * C * 2, base + 2 * H * C * 2, dq_accum.data_ptr<float>(), B, T, H, C, q.stride(1), k.stride(1), v.stride(1),
+               3 * H * C, num_sms_of(q), stream());
+  return dqkv;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("gemm", &gemm, "tcgen05 bf16 GEMM with fused epilogues");
+  m.def("rmsnorm_fwd", &rmsnorm_fwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("qkln_rope_fwd", &qkln_rope_fwd);
+  m.def("qkln_rope_bwd", &qkln_rope_bwd);
+  m.def("embed_fwd", &embed_fwd);
+  m.def("embed_bwd", &embed_bwd);
+  m.def("ce_chunk", &ce_chunk);
+  m.def("dropout", &dropout);
+  m.def("sumsq_accumulate", &sumsq_accumulate);
+  m.def("adamw_step", &adamw_step);
+  m.def("attn_fwd", &attn_fwd);
+  m.def("attn_bwd", &attn_bwd);
+}

@@ -1,0 +1,506 @@
+// Memory-bound kernels of the model (everything that is not a GEMM or attention), sm_100a.
+//   rmsnorm fwd/bwd (K2), QK-LayerNorm + RoPE fwd/bwd (K4,K5), embedding gather / scatter-add (K1),
+//   cross-entropy over a logits chunk (K11), Philox dropout (K12), fused clip+Adam+WD+LR+bf16-cast (K13-K18),
+//   sum-of-squares (K15).
+// All of them are single-pass over HBM with 16-byte vector accesses and fp32 math.
+#include "common.cuh"
+
+#include <curand_philox4x32_x.h>
+#include <stdexcept>
+#include <string>
+
+namespace mg {
+
+static inline void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm (weightless).  One warp per row, the row is kept in registers (D <= 32*8*MAXV elements).
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          float* __restrict__ rstd_out, int M, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nvec = D >> 3;  // uint4 = 8 bf16
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(warp) * D);
+  uint4 v[MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      v[i] = __ldg(xr + j);
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = unpack_bf16(u[e]);
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  const float r = rsqrtf(ss / D + eps);
+  if (lane == 0) rstd_out[warp] = r;
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(warp) * D);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = unpack_bf16(u[e]);
+        o[e] = pack_bf16(f.x * r, f.y * r);
+      }
+      yr[j] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// dx = rstd * (dy - yhat * mean(dy*yhat)) (+ dres),  yhat = x * rstd
+template <int MAXV>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                          const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
+                                                          __nv_bfloat16* __restrict__ dx, int M, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nvec = D >> 3;
+  const size_t off = static_cast<size_t>(warp) * D;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + off);
+  const uint4* gr = reinterpret_cast<const uint4*>(dy + off);
+  const float r = rstd[warp];
+  uint4 xv[MAXV], gv[MAXV];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      xv[i] = __ldg(xr + j);
+      gv[i] = __ldg(gr + j);
+      const uint32_t xu[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+      const uint32_t gu[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 a = unpack_bf16(xu[e]), g = unpack_bf16(gu[e]);
+        dot += g.x * a.x * r + g.y * a.y * r;
+      }
+    }
+  }
+  dot = warp_sum(dot) / D;
+  uint4* outr = reinterpret_cast<uint4*>(dx + off);
+  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + off) : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      const uint32_t xu[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+      const uint32_t gu[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+      uint4 rv = rr ? __ldg(rr + j) : make_uint4(0, 0, 0, 0);
+      const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 a = unpack_bf16(xu[e]), g = unpack_bf16(gu[e]), d = unpack_bf16(ru[e]);
+        float o0 = r * (g.x - a.x * r * dot) + d.x;
+        float o1 = r * (g.y - a.y * r * dot) + d.y;
+        o[e] = pack_bf16(o0, o1);
+      }
+      outr[j] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <typename F>
+static void dispatch_maxv(int D, F&& f) {
+  const int nvec = D / 8;
+  if (D % 8) throw std::runtime_error("rmsnorm: D must be a multiple of 8");
+  if (nvec <= 32) f(std::integral_constant<int, 1>());
+  else if (nvec <= 64) f(std::integral_constant<int, 2>());
+  else if (nvec <= 128) f(std::integral_constant<int, 4>());
+  else if (nvec <= 256) f(std::integral_constant<int, 8>());
+  else if (nvec <= 512) f(std::integral_constant<int, 16>());
+  else throw std::runtime_error("rmsnorm: D > 4096 not supported");
+}
+
+void rmsnorm_fwd(const void* x, void* y, float* rstd, int M, int D, float eps, cudaStream_t s) {
+  dispatch_maxv(D, [&](auto mv) {
+    constexpr int MAXV = decltype(mv)::value;
+    rmsnorm_fwd_kernel<MAXV><<<(M + 7) / 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), rstd, M, D, eps);
+  });
+  check_launch("rmsnorm_fwd");
+}
+void rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* dres, void* dx, int M, int D, cudaStream_t s) {
+  dispatch_maxv(D, [&](auto mv) {
+    constexpr int MAXV = decltype(mv)::value;
+    rmsnorm_bwd_kernel<MAXV><<<(M + 7) / 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), rstd,
+                                                          static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), M, D);
+  });
+  check_launch("rmsnorm_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// QK-LayerNorm (gain only, shared across heads) + interleaved RoPE.
+// One warp per (token, q|k, head) vector of C elements; lane holds EPL = C/32 consecutive elements
+// (EPL even => RoPE pairs never straddle lanes).  sin/cos come from a [T, C/2] fp32 table.
+// Input  qkv  [M, 3, H, C] bf16 (raw projection);  output qk [M, 2, H, C] bf16;  stats [M, 2, H, 2] fp32.
+// ------------------------------------------------------------------------------------------------
+template <int EPL>
+__global__ void __launch_bounds__(256) qkln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ q_gain,
+                                                            const float* __restrict__ k_gain, const float* __restrict__ sin_t,
+                                                            const float* __restrict__ cos_t, __nv_bfloat16* __restrict__ qk,
+                                                            float* __restrict__ stats, long long nvec, int T, int H, float eps) {
+  constexpr int C = EPL * 32;
+  const long long vec = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (vec >= nvec) return;
+  const int h = vec % H;
+  const int which = (vec / H) & 1;          // 0 = q, 1 = k
+  const long long m = vec / (2 * H);
+  const int pos = m % T;
+  const __nv_bfloat16* src = qkv + (m * 3 + which) * H * C + static_cast<long long>(h) * C + lane * EPL;
+  float v[EPL];
+  if (EPL == 2) {
+    float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(src));
+    v[0] = f.x; v[1] = f.y;
+  } else {
+    uint2 u = *reinterpret_cast<const uint2*>(src);
+    float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) s += v[e];
+  const float mu = warp_sum(s) / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) { v[e] -= mu; ss += v[e] * v[e]; }
+  const float rs = rsqrtf(warp_sum(ss) / C + eps);
+  const float* gain = which ? k_gain : q_gain;
+  float o[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; e += 2) {
+    const int c = lane * EPL + e;
+    const float a = v[e] * rs * gain[c], b = v[e + 1] * rs * gain[c + 1];
+    const float sn = sin_t[pos * (C / 2) + c / 2], cs = cos_t[pos * (C / 2) + c / 2];
+    o[e] = a * cs - b * sn;
+    o[e + 1] = b * cs + a * sn;
+  }
+  __nv_bfloat16* dst = qk + (m * 2 + which) * H * C + static_cast<long long>(h) * C + lane * EPL;
+  if (EPL == 2) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(o[0], o[1]);
+  else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+  if (lane == 0) {
+    stats[vec * 2] = mu;
+    stats[vec * 2 + 1] = rs;
+  }
+}
+
+// In place on dqkv [M, 3, H, C] (q and k thirds): d(roped, normalised) -> d(raw projection output).
+// Gain gradients are accumulated per lane over a grid-stride loop, reduced through shared memory, then atomically added.
+template <int EPL>
+__global__ void __launch_bounds__(256) qkln_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, const __nv_bfloat16* __restrict__ qkv_raw,
+                                                            const float* __restrict__ stats, const float* __restrict__ q_gain,
+                                                            const float* __restrict__ k_gain, const float* __restrict__ sin_t,
+                                                            const float* __restrict__ cos_t, float* __restrict__ dq_gain,
+                                                            float* __restrict__ dk_gain, long long nvec, int T, int H) {
+  constexpr int C = EPL * 32;
+  __shared__ float red[2][C];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float gacc[2][EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) gacc[0][e] = gacc[1][e] = 0.f;
+  for (long long vec = warp0; vec < nvec; vec += nwarps) {
+    const int h = vec % H;
+    const int which = (vec / H) & 1;
+    const long long m = vec / (2 * H);
+    const int pos = m % T;
+    const long long off = (m * 3 + which) * H * C + static_cast<long long>(h) * C + lane * EPL;
+    float g[EPL], x[EPL];
+    if (EPL == 2) {
+      float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(dqkv + off));
+      float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(qkv_raw + off));
+      g[0] = a.x; g[1] = a.y; x[0] = b.x; x[1] = b.y;
+    } else {
+      uint2 a = *reinterpret_cast<const uint2*>(dqkv + off);
+      uint2 b = *reinterpret_cast<const uint2*>(qkv_raw + off);
+      float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y);
+      g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y;
+      x[0] = b0.x; x[1] = b0.y; x[2] = b1.x; x[3] = b1.y;
+    }
+    const float mu = stats[vec * 2], rs = stats[vec * 2 + 1];
+    const float* gain = which ? k_gain : q_gain;
+    float dxh[EPL], xh[EPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; e += 2) {
+      const int c = lane * EPL + e;
+      const float sn = sin_t[pos * (C / 2) + c / 2], cs = cos_t[pos * (C / 2) + c / 2];
+      const float dn0 = g[e] * cs + g[e + 1] * sn;        // inverse rotation
+      const float dn1 = g[e + 1] * cs - g[e] * sn;
+      xh[e] = (x[e] - mu) * rs;
+      xh[e + 1] = (x[e + 1] - mu) * rs;
+      gacc[which][e] += dn0 * xh[e];
+      gacc[which][e + 1] += dn1 * xh[e + 1];
+      dxh[e] = dn0 * gain[c];
+      dxh[e + 1] = dn1 * gain[c + 1];
+      s1 += dxh[e] + dxh[e + 1];
+      s2 += dxh[e] * xh[e] + dxh[e + 1] * xh[e + 1];
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    float o[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) o[e] = rs * (dxh[e] - s1 - xh[e] * s2);
+    if (EPL == 2) *reinterpret_cast<uint32_t*>(dqkv + off) = pack_bf16(o[0], o[1]);
+    else *reinterpret_cast<uint2*>(dqkv + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+  }
+#pragma unroll
+  for (int w = 0; w < 2; ++w)
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) atomicAdd(&red[w][lane * EPL + e], gacc[w][e]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dq_gain + i, red[0][i]);
+    atomicAdd(dk_gain + i, red[1][i]);
+  }
+}
+
+void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const float* sin_t, const float* cos_t, void* qk,
+                   float* stats, long long M, int T, int H, int C, float eps, cudaStream_t s) {
+  const long long nvec = M * 2 * H;
+  const unsigned grid = static_cast<unsigned>((nvec + 7) / 8);
+  if (C == 64)
+    qkln_rope_fwd_kernel<2><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
+  else if (C == 128)
+    qkln_rope_fwd_kernel<4><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
+  else throw std::runtime_error("qkln_rope: head_dim must be 64 or 128");
+  check_launch("qkln_rope_fwd");
+}
+void qkln_rope_bwd(void* dqkv, const void* qkv_raw, const float* stats, const float* qg, const float* kg, const float* sin_t,
+                   const float* cos_t, float* dqg, float* dkg, long long M, int T, int H, int C, int num_sms, cudaStream_t s) {
+  const long long nvec = M * 2 * H;
+  const unsigned grid = static_cast<unsigned>(num_sms * 8);
+  if (C == 64)
+    qkln_rope_bwd_kernel<2><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
+  else if (C == 128)
+    qkln_rope_bwd_kernel<4><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
+  else throw std::runtime_error("qkln_rope: head_dim must be 64 or 128");
+  check_launch("qkln_rope_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Embedding gather and scatter-add
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_fwd_kernel(const __nv_bfloat16* __restrict__ wte, const int* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                                 long long M, int D) {
+  const int nvec = D >> 3;
+  const long long total = M * nvec;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / nvec;
+    const int j = i - m * nvec;
+    reinterpret_cast<uint4*>(out + m * D)[j] = __ldg(reinterpret_cast<const uint4*>(wte + static_cast<long long>(idx[m]) * D) + j);
+  }
+}
+__global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const int* __restrict__ idx, float* __restrict__ dwte,
+                                 long long M, int D) {
+  const int nvec = D >> 2;  // 4 elements per thread-iteration
+  const long long total = M * nvec;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / nvec;
+    const int j = i - m * nvec;
+    uint2 u = __ldg(reinterpret_cast<const uint2*>(dx + m * D) + j);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    float4* dst = reinterpret_cast<float4*>(dwte + static_cast<long long>(idx[m]) * D) + j;
+    atomicAdd(dst, make_float4(a.x, a.y, b.x, b.y));
+  }
+}
+void embed_fwd(const void* wte, const int* idx, void* out, long long M, int D, int num_sms, cudaStream_t s) {
+  embed_fwd_kernel<<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(wte), idx, static_cast<__nv_bfloat16*>(out), M, D);
+  check_launch("embed_fwd");
+}
+void embed_bwd(const void* dx, const int* idx, float* dwte, long long M, int D, int num_sms, cudaStream_t s) {
+  embed_bwd_kernel<<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dx), idx, dwte, M, D);
+  check_launch("embed_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-entropy over a chunk of bf16 logits [rows, V] (row stride ldl): loss_sum += Σ(lse - logit[target]);
+// optionally overwrite the logits in place with grad_scale * (softmax - onehot) (bf16) for the backward GEMMs.
+// One 512-thread block per row; online (max, sum) in a single read, second pass served from L2.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) ce_chunk_kernel(__nv_bfloat16* __restrict__ logits, long long ldl, const int* __restrict__ targets,
+                                                       float* __restrict__ loss_sum, int V, float grad_scale, int write_grad) {
+  __shared__ float s_max[16], s_sum[16];
+  __shared__ float s_bcast[2];
+  const long long row = blockIdx.x;
+  __nv_bfloat16* lr = logits + row * ldl;
+  const int nvec = V >> 3;
+  float mx = -INFINITY, sm = 0.f;
+  for (int j = threadIdx.x; j < nvec; j += blockDim.x) {
+    uint4 u = *reinterpret_cast<const uint4*>(lr + j * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float2 t = unpack_bf16(w[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+    float lm = f[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) lm = fmaxf(lm, f[e]);
+    const float nm = fmaxf(mx, lm);
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += __expf(f[e] - nm);
+    sm = sm * __expf(mx - nm) + acc;
+    mx = nm;
+  }
+  for (int j = nvec * 8 + threadIdx.x; j < V; j += blockDim.x) {   // tail (V % 8)
+    const float f = __bfloat162float(lr[j]);
+    const float nm = fmaxf(mx, f);
+    sm = sm * __expf(mx - nm) + __expf(f - nm);
+    mx = nm;
+  }
+  // block reduce (max, sum)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wm = warp_max(mx);
+  float ws = warp_sum(sm * ((mx == -INFINITY) ? 0.f : __expf(mx - wm)));
+  if (lane == 0) { s_max[warp] = wm; s_sum[warp] = ws; }
+  __syncthreads();
+  if (warp == 0) {
+    float m2 = lane < (blockDim.x >> 5) ? s_max[lane] : -INFINITY;
+    float s2 = lane < (blockDim.x >> 5) ? s_sum[lane] : 0.f;
+    const float bm = warp_max(m2);
+    const float bs = warp_sum(s2 * ((m2 == -INFINITY) ? 0.f : __expf(m2 - bm)));
+    if (lane == 0) { s_bcast[0] = bm; s_bcast[1] = bs; }
+  }
+  __syncthreads();
+  const float bm = s_bcast[0], bs = s_bcast[1];
+  const float lse = bm + __logf(bs);
+  const int tgt = targets[row];
+  if (threadIdx.x == 0) atomicAdd(loss_sum, lse - __bfloat162float(lr[tgt]));
+  if (!write_grad) return;
+  const float inv = 1.f / bs;
+  __syncthreads();   // the target logit has been read by thread 0 before anyone overwrites it
+  for (int j = threadIdx.x; j < nvec; j += blockDim.x) {
+    uint4 u = *reinterpret_cast<const uint4*>(lr + j * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 t = unpack_bf16(w[e]);
+      const int c = j * 8 + 2 * e;
+      float g0 = __expf(t.x - bm) * inv - (c == tgt ? 1.f : 0.f);
+      float g1 = __expf(t.y - bm) * inv - (c + 1 == tgt ? 1.f : 0.f);
+      o[e] = pack_bf16(g0 * grad_scale, g1 * grad_scale);
+    }
+    *reinterpret_cast<uint4*>(lr + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  for (int j = nvec * 8 + threadIdx.x; j < V; j += blockDim.x) {
+    const float f = __bfloat162float(lr[j]);
+    lr[j] = __float2bfloat16((__expf(f - bm) * inv - (j == tgt ? 1.f : 0.f)) * grad_scale);
+  }
+}
+void ce_chunk(void* logits, long long ldl, const int* targets, float* loss_sum, int rows, int V, float grad_scale,
+              int write_grad, cudaStream_t s) {
+  ce_chunk_kernel<<<rows, 512, 0, s>>>(static_cast<__nv_bfloat16*>(logits), ldl, targets, loss_sum, V, grad_scale, write_grad);
+  check_launch("ce_chunk");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dropout: y = x * keep / (1-p), keep ~ Bernoulli(1-p) from Philox4x32-10 keyed by (seed, element/4)
+// ------------------------------------------------------------------------------------------------
+__global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4, float p,
+                               unsigned long long seed) {
+  const float scale = 1.f / (1.f - p);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 ctr = make_uint4(static_cast<unsigned>(i), static_cast<unsigned>(i >> 32), 0u, 0u);
+    uint2 key = make_uint2(static_cast<unsigned>(seed), static_cast<unsigned>(seed >> 32));
+    uint4 rnd = curand_Philox4x32_10(ctr, key);
+    uint2 u = __ldg(reinterpret_cast<const uint2*>(x) + i);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    const float th = p * 4294967296.f;
+    a.x = (static_cast<float>(rnd.x) >= th) ? a.x * scale : 0.f;
+    a.y = (static_cast<float>(rnd.y) >= th) ? a.y * scale : 0.f;
+    b.x = (static_cast<float>(rnd.z) >= th) ? b.x * scale : 0.f;
+    b.y = (static_cast<float>(rnd.w) >= th) ? b.y * scale : 0.f;
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16(a.x, a.y), pack_bf16(b.x, b.y));
+  }
+}
+void dropout(const void* x, void* y, long long n, float p, unsigned long long seed, int num_sms, cudaStream_t s) {
+  if (n % 4) throw std::runtime_error("dropout: numel must be a multiple of 4");
+  dropout_kernel<<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n / 4, p, seed);
+  check_launch("dropout");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer: Σ g² and the fused clip · Adam · independent-WD · LR · bf16 cast sweep over one fp32 shard
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ out) {
+  __shared__ float part[16];
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+void sumsq_accumulate(const float* g, long long n, float* out, int num_sms, cudaStream_t s) {
+  if (n % 4) throw std::runtime_error("sumsq: numel must be a multiple of 4");
+  sumsq_kernel<<<num_sms * 2, 512, 0, s>>>(g, n / 4, out);
+  check_launch("sumsq");
+}
+
+struct AdamArgs {
+  float lr, b1, b2, eps, wd_over_lr_peak, inv_bc1, inv_bc2;
+};
+
+// clip = *clip_ptr (device scalar: min(1, 1/||g||)), so the host never waits for the norm.
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                    float* __restrict__ g, __nv_bfloat16* __restrict__ p_lp, long long n4,
+                                                    const float* __restrict__ clip_ptr, AdamArgs a, int zero_grad) {
+  const float clip = *clip_ptr;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float4 gv = reinterpret_cast<float4*>(g)[i];
+    float pp[4] = {pv.x, pv.y, pv.z, pv.w}, mm[4] = {mv.x, mv.y, mv.z, mv.w}, vv_[4] = {vv.x, vv.y, vv.z, vv.w};
+    const float gg[4] = {gv.x * clip, gv.y * clip, gv.z * clip, gv.w * clip};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      mm[e] = a.b1 * mm[e] + (1.f - a.b1) * gg[e];
+      vv_[e] = a.b2 * vv_[e] + (1.f - a.b2) * gg[e] * gg[e];
+      const float u = (mm[e] * a.inv_bc1) / (sqrtf(vv_[e] * a.inv_bc2) + a.eps) + a.wd_over_lr_peak * pp[e];
+      pp[e] -= a.lr * u;
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vv_[0], vv_[1], vv_[2], vv_[3]);
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p_lp) reinterpret_cast<uint2*>(p_lp)[i] = make_uint2(pack_bf16(pp[0], pp[1]), pack_bf16(pp[2], pp[3]));
+  }
+}
+void adamw_step(float* p, float* m, float* v, float* g, void* p_lp, long long n, const float* clip_ptr, float lr, float b1,
+                float b2, float eps, float wd_over_lr_peak, float bc1, float bc2, int zero_grad, int num_sms, cudaStream_t s) {
+  if (n % 4) throw std::runtime_error("adamw: numel must be a multiple of 4");
+  AdamArgs a{lr, b1, b2, eps, wd_over_lr_peak, 1.f / bc1, 1.f / bc2};
+  adamw_kernel<<<num_sms * 8, 256, 0, s>>>(p, m, v, g, static_cast<__nv_bfloat16*>(p_lp), n / 4, clip_ptr, a, zero_grad);
+  check_launch("adamw");
+}
+
+}  // namespace mg

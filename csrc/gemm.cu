@@ -1,0 +1,379 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// (fp32 accumulators in TMEM, double buffered) -> tcgen05.ld epilogue -> swizzled smem -> TMA store.
+//
+//   D[M,N] (+)= A[M,K] · B[N,K]^T          A, B bf16; each operand either K-major or MN-major in memory
+//
+// One kernel family serves every linear layer of the model:
+//   forward   y  = x · Wᵀ           A K-major,  B K-major   (+ residual | + tanh-GELU dual output)
+//   dgrad     dx = dy · W           A K-major,  B MN-major  (· gelu'(pre) for the MLP up-projection)
+//   wgrad     dW += dyᵀ · x         A MN-major, B MN-major  fp32 output, TMA reduce-add accumulation
+//
+// Roles (192 threads, 1 CTA / SM, grid = #SMs, static persistent tile schedule with M-grouping for L2 reuse):
+//   warp 0   TMA producer   (one elected lane)
+//   warp 1   TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warp 2-5 epilogue: TMEM -> registers -> epilogue math -> smem staging -> TMA store / reduce-add
+// Pipelines: smem ring (full/empty mbarriers, 4 stages of 128x64 A + 256x64 B), TMEM ring (2 x 256 columns).
+#include "common.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <stdexcept>
+#include <string>
+
+namespace mg {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;             // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;             // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int CSTAGE_BYTES = BM * 128;                 // 128 rows x 128 B (64 bf16 or 32 fp32 per row)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 256 + 1024;  // + barriers + align slack
+constexpr int GROUP_M = 8;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+
+enum Epilogue : int {
+  EPI_STORE = 0,      // D = acc                       (bf16)
+  EPI_RESIDUAL = 1,   // D = acc + AUX                 (bf16)
+  EPI_GELU = 2,       // D = acc, D2 = gelu(acc)       (bf16, bf16)
+  EPI_DGELU = 3,      // D = acc * gelu'(AUX)          (bf16)
+  EPI_F32 = 4,        // D (+)= acc                    (fp32; accumulate via TMA reduce-add)
+};
+
+struct GemmParams {
+  const __nv_bfloat16* aux;
+  long long ld_aux;
+  int M, N, K;
+  int accumulate;
+};
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
+                  const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sC = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + 2 * CSTAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    if (EPI == EPI_GELU) tma_prefetch_desc(&tmD2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], EPI_THREADS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    const int per_group = GROUP_M * num_n;
+    const int g = tile / per_group;
+    const int first_m = g * GROUP_M;
+    const int gsize = min(num_m - first_m, GROUP_M);
+    const int r = tile - g * per_group;
+    m_blk = first_m + r % gsize;
+    n_blk = r / gsize;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, m_blk, n_blk);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t tphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], tphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(a_base + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc(a_base + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc(b_base + k * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);        // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                // row inside the 128-row tile
+    const bool issuer = (threadIdx.x == 64);      // first epilogue thread issues the TMA stores
+    const uint32_t sw = (row & 7);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blk, n_blk);
+      const int buf = it & 1;
+      const uint32_t tphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[buf], tphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      const long long grow = static_cast<long long>(m_blk) * BM + row;
+
+      if (EPI == EPI_F32) {
+        // 8 chunks of 32 fp32 columns (128 B per row)
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint8_t* sbuf = sC + (c & 1) * CSTAGE_BYTES;
+          if (issuer) tma_wait_group_read<1>();
+          named_bar_sync(1, EPI_THREADS);
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          uint8_t* rowp = sbuf + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = v;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, EPI_THREADS);
+          if (issuer) {
+            const int c0 = n_blk * BN + c * 32;
+            if (c0 < p.N) {
+              if (p.accumulate) tma_reduce_add_2d(&tmD, sbuf, c0, m_blk * BM);
+              else tma_store_2d(&tmD, sbuf, c0, m_blk * BM);
+            }
+            tma_commit_group();
+          }
+        }
+      } else {
+        // 4 chunks of 64 bf16 columns (128 B per row)
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint8_t* sbuf = (EPI == EPI_GELU) ? sC : sC + (c & 1) * CSTAGE_BYTES;
+          uint8_t* sbuf2 = sC + CSTAGE_BYTES;
+          if (issuer) {
+            if (EPI == EPI_GELU) tma_wait_group_read<0>();
+            else tma_wait_group_read<1>();
+          }
+          named_bar_sync(1, EPI_THREADS);
+          uint32_t r[64];
+          {
+            uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+            uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+            tmem_ld_x32(t_row + c * 64, r0);
+            tmem_ld_x32(t_row + c * 64 + 32, r1);
+            tmem_ld_wait();
+          }
+          const int col0 = n_blk * BN + c * 64;
+          const bool valid = (grow < p.M) && (col0 < p.N);
+          uint8_t* rowp = sbuf + row * 128;
+          if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + grow * p.ld_aux + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 a = valid ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
+              uint32_t au[4] = {a.x, a.y, a.z, a.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 av = unpack_bf16(au[e]);
+                float x0 = __uint_as_float(r[8 * j + 2 * e]), x1 = __uint_as_float(r[8 * j + 2 * e + 1]);
+                if (EPI == EPI_RESIDUAL) { x0 += av.x; x1 += av.y; }
+                else { x0 *= gelu_tanh_grad(av.x); x1 *= gelu_tanh_grad(av.y); }
+                o[e] = pack_bf16(x0, x1);
+              }
+              *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          } else {
+            uint8_t* rowp2 = sbuf2 + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t o[4], g[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x0 = __uint_as_float(r[8 * j + 2 * e]), x1 = __uint_as_float(r[8 * j + 2 * e + 1]);
+                o[e] = pack_bf16(x0, x1);
+                if (EPI == EPI_GELU) {
+                  // GELU of the *rounded* pre-activation so that backward (which only sees bf16 pre) is consistent
+                  float2 xr = unpack_bf16(o[e]);
+                  g[e] = pack_bf16(gelu_tanh(xr.x), gelu_tanh(xr.y));
+                }
+              }
+              *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              if (EPI == EPI_GELU) *reinterpret_cast<uint4*>(rowp2 + ((j ^ sw) << 4)) = make_uint4(g[0], g[1], g[2], g[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, EPI_THREADS);
+          if (issuer) {
+            if (col0 < p.N) {
+              tma_store_2d(&tmD, sbuf, col0, m_blk * BM);
+              if (EPI == EPI_GELU) tma_store_2d(&tmD2, sbuf2, col0, m_blk * BM);
+            }
+            tma_commit_group();
+          }
+        }
+      }
+      // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);
+    }
+    if (issuer) tma_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launcher
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* ptr = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || ptr == nullptr) throw std::runtime_error("cuTensorMapEncodeTiled entry point not found");
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] (cols contiguous, leading dimension ld elements), 128B swizzle.
+CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, long long rows, long long cols, long long ld, int box_cols,
+                         int box_rows) {
+  using Key = std::tuple<const void*, int, long long, long long, long long, int, int>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key{ptr, elem_bytes, rows, cols, ld, box_cols, box_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = get_encode()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ") rows=" +
+                             std::to_string(rows) + " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld));
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  return m;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tD2,
+                       const GemmParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tA, tB, tD, tD2, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("gemm launch: ") + cudaGetErrorString(e));
+}
+
+// a: [M,K] row-major (a_mn=0) or [K,M] row-major (a_mn=1);  b: [N,K] (b_mn=0) or [K,N] (b_mn=1)
+// d: [M,N] bf16 (fp32 for EPI_F32); d2: second bf16 output for EPI_GELU; aux: [M,N] bf16 for RESIDUAL / DGELU.
+void gemm_launch(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d,
+                 long long ldd, void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K,
+                 int epi, int accumulate, int num_sms, cudaStream_t stream) {
+  CUtensorMap tA = a_mn ? make_tmap_2d(a, 2, K, M, lda, 64, BK) : make_tmap_2d(a, 2, M, K, lda, BK, BM);
+  CUtensorMap tB = b_mn ? make_tmap_2d(b, 2, K, N, ldb, 64, BK) : make_tmap_2d(b, 2, N, K, ldb, BK, BN);
+  CUtensorMap tD = (epi == EPI_F32) ? make_tmap_2d(d, 4, M, N, ldd, 32, BM) : make_tmap_2d(d, 2, M, N, ldd, 64, BM);
+  CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate};
+#define MG_CASE(AM, BM_, E) \
+  if (a_mn == AM && b_mn == BM_ && epi == E) return launch_one<AM, BM_, E>(tA, tB, tD, tD2, p, num_sms, stream);
+  MG_CASE(false, false, EPI_STORE)
+  MG_CASE(false, false, EPI_RESIDUAL)
+  MG_CASE(false, false, EPI_GELU)
+  MG_CASE(false, false, EPI_F32)
+  MG_CASE(false, true, EPI_STORE)
+  MG_CASE(false, true, EPI_DGELU)
+  MG_CASE(false, true, EPI_RESIDUAL)
+  MG_CASE(true, true, EPI_F32)
+  MG_CASE(true, true, EPI_STORE)
+  MG_CASE(true, false, EPI_F32)
+#undef MG_CASE
+  throw std::runtime_error("gemm_launch: unsupported (a_mn, b_mn, epilogue) combination");
+}
+
+}  // namespace mg
