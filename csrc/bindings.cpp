@@ -27,6 +27,13 @@ void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, 
 void attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* delta,
               void* dq, void* dk, void* dv, float* dq_accum, int B, int T, int H, int C, long long q_row_stride,
               long long k_row_stride, long long v_row_stride, long long dqkv_row_stride, int num_sms, cudaStream_t s);
+void xrank_barrier(const long long* pad_ptrs, int rank, int world, int slot, unsigned epoch, cudaStream_t s);
+void rs_sumsq(const long long* grad_ptrs, long long mc_ptr, float* out_shard, float* sumsq, long long shard_off, long long n, int rank,
+              int world, int num_sms, cudaStream_t s);
+void adamw_allgather(float* p, float* m, float* v, const float* g, const long long* lp_ptrs, long long mc_ptr, long long shard_off,
+                     long long n, const float* clip_ptr, float lr, float b1, float b2, float eps, float wd_over_lr_peak, float bc1,
+                     float bc2, int world, int num_sms, cudaStream_t s);
+void ag_pull(const long long* lp_ptrs, void* local, long long shard_elems, int rank, int world, unsigned* flags, int n_ctas, cudaStream_t s);
 }  // namespace mg
 
 namespace {
@@ -200,6 +207,37 @@ at::Tensor attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& 
   return dqkv;
 }
 
+// ---- in-kernel NVLink communication (csrc/comm.cu).  Pointer lists are raw device addresses of the peers' symmetric buffers.
+void xrank_barrier(std::vector<int64_t> pads, int64_t rank, int64_t slot, int64_t epoch) {
+  std::vector<long long> p(pads.begin(), pads.end());
+  mg::xrank_barrier(p.data(), rank, static_cast<int>(p.size()), slot, static_cast<unsigned>(epoch), stream());
+}
+void rs_sumsq(std::vector<int64_t> grad_ptrs, int64_t mc_ptr, at::Tensor& out_shard, at::Tensor& sumsq, int64_t shard_off, int64_t rank) {
+  c10::cuda::CUDAGuard guard(out_shard.device());
+  CHECK_F32(out_shard); CHECK_F32(sumsq);
+  std::vector<long long> p(grad_ptrs.begin(), grad_ptrs.end());
+  mg::rs_sumsq(p.data(), mc_ptr, out_shard.data_ptr<float>(), sumsq.data_ptr<float>(), shard_off, out_shard.numel(), rank,
+               static_cast<int>(p.size()), num_sms_of(out_shard), stream());
+}
+void adamw_allgather(at::Tensor& p, at::Tensor& m, at::Tensor& v, const at::Tensor& g, std::vector<int64_t> lp_ptrs, int64_t mc_ptr,
+                     int64_t shard_off, const at::Tensor& clip, double lr, double b1, double b2, double eps, double wd_over_lr_peak,
+                     double bc1, double bc2) {
+  c10::cuda::CUDAGuard guard(p.device());
+  CHECK_F32(p); CHECK_F32(m); CHECK_F32(v); CHECK_F32(g); CHECK_F32(clip);
+  std::vector<long long> pp(lp_ptrs.begin(), lp_ptrs.end());
+  mg::adamw_allgather(p.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), g.data_ptr<float>(), pp.data(), mc_ptr, shard_off,
+                      p.numel(), clip.data_ptr<float>(), static_cast<float>(lr), static_cast<float>(b1), static_cast<float>(b2),
+                      static_cast<float>(eps), static_cast<float>(wd_over_lr_peak), static_cast<float>(bc1), static_cast<float>(bc2),
+                      static_cast<int>(pp.size()), num_sms_of(p), stream());
+}
+void ag_pull(std::vector<int64_t> lp_ptrs, at::Tensor& local, int64_t shard_elems, int64_t rank, at::Tensor& flags, int64_t n_ctas) {
+  c10::cuda::CUDAGuard guard(local.device());
+  CHECK_BF16(local);
+  std::vector<long long> pp(lp_ptrs.begin(), lp_ptrs.end());
+  mg::ag_pull(pp.data(), local.data_ptr(), shard_elems, rank, static_cast<int>(pp.size()), reinterpret_cast<unsigned*>(flags.data_ptr()),
+              n_ctas, stream());
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -216,4 +254,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adamw_step", &adamw_step);
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_bwd", &attn_bwd);
+  m.def("xrank_barrier", &xrank_barrier);
+  m.def("rs_sumsq", &rs_sumsq);
+  m.def("adamw_allgather", &adamw_allgather);
+  m.def("ag_pull", &ag_pull);
 }

@@ -258,18 +258,21 @@ class FSDPEngine:
                 if u.reduced_event is not None:
                     cur.wait_event(u.reduced_event)
                     u.reduced_event = None
-        sumsq = torch.zeros((), dtype=torch.float32, device=self.device)
-        for u in self.units:
-            sumsq = sumsq + be.sumsq(u.grad_shard).float()
-        if self.S > 1:
-            D.all_reduce_sum(sumsq, self.mesh.shard_group)
-        clip, gnorm = clip_factor_from_sumsq(sumsq)
-        sc = step_scalars(self.count, self.cfg)
-        for u in self.units:
-            be.adamw_step(u.master, u.exp_avg, u.exp_avg_sq, u.grad_shard, u.lp_shard,
-                          lr=sc.lr, b1=sc.b1, b2=sc.b2, eps=sc.eps, wd_over_lr_peak=sc.wd_over_lr_peak,
-                          bc1=sc.bc1, bc2=sc.bc2, grad_scale=clip)
-            u.grad_full.zero_()
+        if self.fused is not None:
+            gnorm = self.fused.optimizer_step()          # RS already pulled per unit; AdamW ⊕ all-gather push
+        else:
+            sumsq = torch.zeros((), dtype=torch.float32, device=self.device)
+            for u in self.units:
+                sumsq = sumsq + be.sumsq(u.grad_shard).float()
+            if self.S > 1:
+                D.all_reduce_sum(sumsq, self.mesh.shard_group)
+            clip, gnorm = clip_factor_from_sumsq(sumsq)
+            sc = step_scalars(self.count, self.cfg)
+            for u in self.units:
+                be.adamw_step(u.master, u.exp_avg, u.exp_avg_sq, u.grad_shard, u.lp_shard,
+                              lr=sc.lr, b1=sc.b1, b2=sc.b2, eps=sc.eps, wd_over_lr_peak=sc.wd_over_lr_peak,
+                              bc1=sc.bc1, bc2=sc.bc2, grad_scale=clip)
+                u.grad_full.zero_()
         if self.cuda:
             self._opt_done_event = torch.cuda.Event()
             self._opt_done_event.record(torch.cuda.current_stream())

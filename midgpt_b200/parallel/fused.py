@@ -1,0 +1,114 @@
+"""In-kernel NVLink communication for the FSDP engine (``comm="fused"``) — the product path; NCCL is the baseline.
+
+Symmetric memory (``torch.distributed._symmetric_memory``: identical allocations on every rank, peer-mapped
+through NVSwitch, optional NVLS multicast address) holds two arenas:
+
+* ``grad_arena``  fp32 — every unit's full local gradient accumulator (what wgrad GEMMs add into);
+* ``lp_arena``    bf16 — every unit's gathered compute weights (what forward/backward GEMMs read).
+
+With both arenas peer-visible the two FSDP collectives disappear into kernels that were needed anyway
+(csrc/comm.cu):
+
+* ``rs_sumsq``         reduce-scatter ⊕ mean ⊕ Σg²: each rank *pulls* its shard of all peers' accumulators
+                       (``multimem.ld_reduce`` = in-switch add when multicast is available, P2P loads otherwise);
+* ``adamw_allgather``  clip·Adam·WD·LR on the fp32 shard, bf16 result *pushed* into every rank's ``lp_arena``
+                       (``multimem.st`` or P2P stores) — the optimizer step is the all-gather.
+
+Ordering uses a device-side all-ranks barrier kernel (system-scope release/acquire flags in a symmetric pad):
+per unit before its pull (all ranks finished that unit's backward), once after all pulls (accumulators may
+be zeroed), once after all pushes (weights visible everywhere).  No NCCL call moves tensor data; NCCL
+carries only the 4-byte Σg² all-reduce.
+"""
+from __future__ import annotations
+
+import typing as tp
+
+import torch
+import torch.distributed as dist
+
+from ..optim import step_scalars, clip_factor_from_sumsq
+
+
+class FusedComm:
+    def __init__(self, engine):
+        import torch.distributed._symmetric_memory as symm_mem
+        from ..ops.b200_backend import load_ext
+        if engine.gather_mode != "step":
+            raise RuntimeError('comm="fused" keeps bf16 weights resident: use gather_mode="step" (or "auto")')
+        self.ext = load_ext()
+        self.e = engine
+        mesh = engine.mesh
+        self.rank, self.world = mesh.shard_rank, mesh.shard_size
+        group = mesh.shard_group
+        dev = engine.device
+        total = sum(u.padded for u in engine.units)
+        self.grad_arena = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        self.lp_arena = symm_mem.empty(total, dtype=engine.compute_dtype, device=dev)
+        self.pad = symm_mem.empty(4096, dtype=torch.int32, device=dev)
+        self.grad_arena.zero_()
+        self.lp_arena.zero_()
+        self.pad.zero_()
+        torch.cuda.synchronize()
+        self.h_grad = symm_mem.rendezvous(self.grad_arena, group)
+        self.h_lp = symm_mem.rendezvous(self.lp_arena, group)
+        self.h_pad = symm_mem.rendezvous(self.pad, group)
+        self.grad_ptrs = [int(p) for p in self.h_grad.buffer_ptrs]
+        self.lp_ptrs = [int(p) for p in self.h_lp.buffer_ptrs]
+        self.pad_ptrs = [int(p) for p in self.h_pad.buffer_ptrs]
+        use_mc = bool(int(__import__("os").environ.get("MIDGPT_MULTIMEM", "1")))
+        self.mc_grad = int(self.h_grad.multicast_ptr) if use_mc and self.h_grad.has_multicast_support(dev.type, dev.index) else 0
+        self.mc_lp = int(self.h_lp.multicast_ptr) if use_mc and self.mc_grad else 0
+        self.epoch = 0
+        # re-point the engine's per-unit buffers into the arenas
+        off = 0
+        self.offsets: tp.Dict[int, int] = {}
+        for i, u in enumerate(engine.units):
+            self.offsets[i] = off
+            u.grad_full = self.grad_arena[off:off + u.padded]
+            u.lp_full = self.lp_arena[off:off + u.padded]
+            u.lp_shard = u.lp_full[self.rank * u.shard:(self.rank + 1) * u.shard]
+            u.lp_shard.copy_(u.master)
+            off += u.padded
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._pushed = False
+        self._barrier()          # every rank has zeroed / initialised its arenas
+        if mesh.is_main:
+            print(f"[fused-comm] symmetric arenas: grad {total * 4 / 2**30:.2f} GB fp32, weights {total * 2 / 2**30:.2f} GB bf16, "
+                  f"multicast={'yes' if self.mc_grad else 'no (P2P loads/stores)'}")
+
+    # ------------------------------------------------------------------
+    def _barrier(self) -> None:
+        self.epoch += 1
+        self.ext.xrank_barrier(self.pad_ptrs, self.rank, 0, self.epoch)
+
+    def all_gather(self, u) -> None:
+        """Only the very first gather (initial weights) moves data here; afterwards AdamW pushes keep lp_arena current."""
+        if self._pushed:
+            return
+        dist.all_gather_into_tensor(u.lp_full, u.lp_shard, group=self.e.mesh.shard_group)
+
+    def reduce_scatter(self, u) -> None:
+        """Called on the comm stream once this rank's backward of unit ``u`` is complete."""
+        i = self.e.units.index(u)
+        self._barrier()                                   # every rank finished accumulating this unit
+        off = self.offsets[i] + self.rank * u.shard
+        self.ext.rs_sumsq(self.grad_ptrs, self.mc_grad, u.grad_shard, self.sumsq, off, self.rank)
+
+    def optimizer_step(self) -> torch.Tensor:
+        """Runs on the engine's compute stream after all reduce events have been waited on."""
+        e = self.e
+        self._barrier()                                   # all pulls everywhere are done -> accumulators reusable
+        self.grad_arena.zero_()
+        total = self.sumsq.clone()
+        self.sumsq.zero_()
+        dist.all_reduce(total, group=e.mesh.shard_group)   # 4 bytes
+        clip, gnorm = clip_factor_from_sumsq(total[0])
+        sc = step_scalars(e.count, e.cfg)
+        clip1 = clip.reshape(1).float()
+        for i, u in enumerate(e.units):
+            off = self.offsets[i] + self.rank * u.shard
+            self.ext.adamw_allgather(u.master, u.exp_avg, u.exp_avg_sq, u.grad_shard, self.lp_ptrs, self.mc_lp, off, clip1,
+                                     sc.lr, sc.b1, sc.b2, sc.eps, sc.wd_over_lr_peak, sc.bc1, sc.bc2)
+        self._barrier()                                   # every rank's pushes have landed everywhere
+        self._pushed = True
+        return gnorm
