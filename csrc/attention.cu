@@ -67,7 +67,7 @@ struct FwdCfg {
   static constexpr int K_BYTES = BKV * C * 2;
   static constexpr int V_BYTES = BKV * C * 2;
   static constexpr int P_BYTES = BQ * BKV * 2;
-  static constexpr int SMEM = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES + 256 + 1024;
+  static constexpr int SMEM = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES + 256;
   static constexpr int TMEM_COLS = 256;
   static constexpr int S_COL = 0, O_COL = BKV;
 };
@@ -79,8 +79,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 int T, int H, float scale) {
   using Cfg = FwdCfg<C>;
   constexpr int BQ = Cfg::BQ, BKV = Cfg::BKV;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B operands need 1024-byte aligned tiles
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + 2 * Cfg::K_BYTES;
@@ -321,7 +322,7 @@ struct BwdCfg {
   static constexpr int BQ = 128, BKV = 128;
   static constexpr int TILE = 128 * C * 2;             // one [128 x C] bf16 operand tile
   static constexpr int PS = 128 * 128 * 2;             // P / dS tiles
-  static constexpr int SMEM = 4 * TILE + 2 * PS + 256 + 1024;   // K, V, Q, dO, P, dS
+  static constexpr int SMEM = 4 * TILE + 2 * PS + 256;   // K, V, Q, dO, P, dS
   static constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + C;   // dQ aliases S
   static constexpr int TMEM_COLS = 512;
 };
@@ -334,8 +335,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long dkv_row_stride, int T, int H,
                 float scale) {
   using Cfg = BwdCfg<C>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B operands need 1024-byte aligned tiles
   uint8_t* sK = smem;
   uint8_t* sV = sK + Cfg::TILE;
   uint8_t* sQ = sV + Cfg::TILE;

@@ -122,7 +122,7 @@ def build_loader(force: bool = False, verbose: bool = True) -> str:
     out = loader_path()
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == digest:
         return out
-    cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", src, "-o", out,
+    cmd = ["g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-fPIC", "-shared", "-pthread", src, "-o", out,
            "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"]]
     _run(cmd)
     with open(stamp, "w") as f:
