@@ -46,6 +46,24 @@ static CUtensorMap make_tmap_bthc(const void* ptr, int B, int T, int H, int C, l
   return m;
 }
 
+// fp32 dQ accumulator [B, T, H*C] as a 3-D map so that query-tile rows past T are clipped instead of spilling into the next batch
+static CUtensorMap make_tmap_dq(const void* ptr, int B, int T, int D) {
+  cudaDriverEntryPointQueryResult q;
+  void* p = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+    throw std::runtime_error("cuTensorMapEncodeTiled entry point not found");
+  PFN_encodeTiled4 fn = reinterpret_cast<PFN_encodeTiled4>(p);
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)D * 4 * T};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("attention: dq tensor map failed: " + std::to_string((int)r));
+  return m;
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -187,20 +205,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       const int kv0 = j * BKV;
       const bool need_mask = (kv0 + BKV - 1 > q0);          // tile touches or crosses the diagonal
+      constexpr int NCH = BKV / 32;
+      constexpr bool KEEP = (BKV == 64);                     // S row stays in registers between the two passes
+      uint32_t sreg[KEEP ? NCH : 1][32];
       // pass 1: row max
       float mx = -INFINITY;
 #pragma unroll
-      for (int ch = 0; ch < BKV / 32; ++ch) {
-        uint32_t r[32];
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t tmp[32];
+        uint32_t(&r)[32] = KEEP ? sreg[KEEP ? ch : 0] : tmp;
         tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
-        tmem_ld_wait();
+        if (!KEEP) {
+          tmem_ld_wait();
+          if (need_mask) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float v = __uint_as_float(r[e]) * sl2;
-          if (need_mask && (kv0 + ch * 32 + e > q_idx)) v = -INFINITY;
-          mx = fmaxf(mx, v);
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (kv0 + ch * 32 + e > q_idx) ? -INFINITY : __uint_as_float(r[e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+          }
         }
       }
+      if (KEEP) {
+        tmem_ld_wait();
+        if (need_mask) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (kv0 + ch * 32 + e > q_idx) ? -INFINITY : __uint_as_float(sreg[KEEP ? ch : 0][e]));
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sreg[KEEP ? ch : 0][e]));
+        }
+      }
+      mx *= sl2;                                             // sl2 > 0: max commutes with the scaling
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);           // O_{j-1} complete; P buffer free
         tc_fence_after();
@@ -223,20 +263,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else {
         m_used = mx;
       }
-      // pass 2: P = exp2(s - m_used) -> bf16 -> swizzled smem (K-major A operand of P·V)
+      // pass 2: P = exp2(s*c - m_used) -> bf16 -> swizzled smem (K-major A operand of P·V)
 #pragma unroll
-      for (int ch = 0; ch < BKV / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
-        tmem_ld_wait();
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t tmp[32];
+        uint32_t(&r)[32] = KEEP ? sreg[KEEP ? ch : 0] : tmp;
+        if (!KEEP) {
+          tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+          tmem_ld_wait();
+        }
         float p[32];
+        if (need_mask) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float v = __uint_as_float(r[e]) * sl2 - m_used;
-          float pe = exp2f(v);
-          if (need_mask && (kv0 + ch * 32 + e > q_idx)) pe = 0.f;
-          p[e] = pe;
-          l += pe;
+          for (int e = 0; e < 32; ++e) {
+            float pe = exp2f(fmaf(__uint_as_float(r[e]), sl2, -m_used));
+            if (kv0 + ch * 32 + e > q_idx) pe = 0.f;
+            p[e] = pe;
+            l += pe;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            p[e] = exp2f(fmaf(__uint_as_float(r[e]), sl2, -m_used));
+            l += p[e];
+          }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -319,19 +369,24 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* 
 
 template <int C>
 struct BwdCfg {
-  static constexpr int BQ = 128, BKV = 128;
   static constexpr int TILE = 128 * C * 2;             // one [128 x C] bf16 operand tile
-  static constexpr int PS = 128 * 128 * 2;             // P / dS tiles
-  static constexpr int SMEM = 4 * TILE + 2 * PS + 256;   // K, V, Q, dO, P, dS
-  static constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + C;   // dQ aliases S
+  static constexpr int PS = 128 * 128 * 2;             // P, then dS, then the dQ staging area (one buffer, reused in turn)
+  static constexpr int SMEM = 6 * TILE + PS + 256;     // K, V, 2 x Q, 2 x dO, P/dS
+  static constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + C;   // dQ aliases dP
   static constexpr int TMEM_COLS = 512;
+  static constexpr int THREADS = 320;                  // 8 compute warps + TMA warp + MMA warp
 };
 
+// Backward.  One CTA = one (batch, head, 128-key tile); loop over query tiles i >= j.
+//   compute warps 0-7: thread = query row (TMEM lane) x column half (warps 0-3: keys 0-63, warps 4-7: keys 64-127)
+//   warp 8: TMA producer (K,V once; Q_i/dO_i double buffered)       warp 9: tcgen05.mma issuer
+// Tensor-pipe order per tile:  dV(i) dK(i) dQ(i) | S(i+1) dP(i+1)  — S(i+1) is issued before dQ(i) is drained
+// (dQ aliases dP, not S), so the P phase of the next tile never waits for the tensor core.
 template <int C>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(BwdCfg<C>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_accum,
+                const __grid_constant__ CUtensorMap tmdQ, const float* __restrict__ lse, const float* __restrict__ delta,
                 __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long dkv_row_stride, int T, int H,
                 float scale) {
   using Cfg = BwdCfg<C>;
@@ -340,22 +395,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B operands need 1024-byte aligned tiles
   uint8_t* sK = smem;
   uint8_t* sV = sK + Cfg::TILE;
-  uint8_t* sQ = sV + Cfg::TILE;
-  uint8_t* sdO = sQ + Cfg::TILE;
-  uint8_t* sP = sdO + Cfg::TILE;
-  uint8_t* sdS = sP + Cfg::PS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + Cfg::PS);
-  uint64_t* kv_full = bars;        // K and V landed
-  uint64_t* q_full = bars + 1;     // Q_i landed
-  uint64_t* do_full = bars + 2;    // dO_i landed
-  uint64_t* qdo_empty = bars + 3;  // Q_i / dO_i no longer read by any MMA
-  uint64_t* s_full = bars + 4;     // S ready
-  uint64_t* dp_full = bars + 5;    // dP ready
-  uint64_t* p_ready = bars + 6;    // P in smem (128 arrivals)
-  uint64_t* ds_ready = bars + 7;   // dS in smem, S/dP fully read (128 arrivals)
-  uint64_t* dq_full = bars + 8;    // dQ tile complete in TMEM (and dV/dK MMAs of this tile retired)
-  uint64_t* dq_drained = bars + 9; // dQ read out (128 arrivals) -> S columns reusable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint8_t* sQ = sV + Cfg::TILE;                  // 2 stages
+  uint8_t* sdO = sQ + 2 * Cfg::TILE;             // 2 stages
+  uint8_t* sPS = sdO + 2 * Cfg::TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPS + Cfg::PS);
+  uint64_t* kv_full = bars;          // K and V landed
+  uint64_t* q_full = bars + 1;       // [2]
+  uint64_t* do_full = bars + 3;      // [2]
+  uint64_t* qdo_empty = bars + 5;    // [2] Q_i / dO_i no longer read by any MMA
+  uint64_t* s_full = bars + 7;
+  uint64_t* dp_full = bars + 8;
+  uint64_t* p_ready = bars + 9;      // 256 arrivals: P in smem, S fully read
+  uint64_t* dv_done = bars + 10;     // dV MMA retired: P buffer may be overwritten with dS
+  uint64_t* ds_ready = bars + 11;    // 256 arrivals: dS in smem, dP fully read
+  uint64_t* dq_full = bars + 12;     // dK / dQ MMAs retired
+  uint64_t* dq_drained = bars + 13;  // 256 arrivals: dQ read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x;                     // key tile (small index = most work, scheduled first)
@@ -365,19 +420,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_it = nq - jt;                      // query tiles jt .. nq-1
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
-    mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(qdo_empty, 1);
-    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 128); mbar_init(ds_ready, 128);
-    mbar_init(dq_full, 1); mbar_init(dq_drained, 128);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&do_full[s], 1); mbar_init(&qdo_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 256); mbar_init(dv_done, 1); mbar_init(ds_ready, 256);
+    mbar_init(dq_full, 1); mbar_init(dq_drained, 256);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
+    // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * Cfg::TILE);
 #pragma unroll
@@ -386,169 +443,198 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_4d(sV + cb * (128 * 128), &tmV, kv_full, cb * 64, h, kv0, b);
       }
       for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
         const int q0 = (jt + it) * 128;
-        mbar_wait(qdo_empty, (it & 1) ^ 1);
-        mbar_expect_tx(q_full, Cfg::TILE);
+        mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], Cfg::TILE);
 #pragma unroll
-        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sQ + cb * (128 * 128), &tmQ, q_full, cb * 64, h, q0, b);
-        mbar_expect_tx(do_full, Cfg::TILE);
+        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sQ + st * Cfg::TILE + cb * (128 * 128), &tmQ, &q_full[st], cb * 64, h, q0, b);
+        mbar_expect_tx(&do_full[st], Cfg::TILE);
 #pragma unroll
-        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sdO + cb * (128 * 128), &tmdO, do_full, cb * 64, h, q0, b);
+        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sdO + st * Cfg::TILE + cb * (128 * 128), &tmdO, &do_full[st], cb * 64, h, q0, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
+    // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP : both operands K-major, N = 128
       constexpr uint32_t idesc_mm = make_idesc_bf16(128, C, 1, 1);     // dV, dK: both MN-major, N = C
       constexpr uint32_t idesc_km = make_idesc_bf16(128, C, 0, 1);     // dQ    : A K-major (dS), B MN-major (K)
-      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), q_base = smem_u32(sQ), do_base = smem_u32(sdO);
-      const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sdS);
-      mbar_wait(kv_full, 0);
-      for (int it = 0; it < n_it; ++it) {
-        const uint32_t ph = it & 1;
-        if (it > 0) { mbar_wait(dq_drained, (it - 1) & 1); }
-        mbar_wait(q_full, ph);
+      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), ps_base = smem_u32(sPS);
+      auto issue_s = [&](int it) {
+        const int st = it & 1;
+        mbar_wait(&q_full[st], (it >> 1) & 1);
         tc_fence_after();
-        // S = Q · Kᵀ
+        const uint32_t q_base = smem_u32(sQ + st * Cfg::TILE);
 #pragma unroll
         for (int k = 0; k < C / 16; ++k) {
           const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
           umma_bf16_ss(tmem + Cfg::S_COL, make_smem_desc(q_base + off, 16, 1024), make_smem_desc(k_base + off, 16, 1024), idesc_kk, k != 0);
         }
         umma_commit(s_full);
-        mbar_wait(do_full, ph);
+      };
+      auto issue_dp = [&](int it) {
+        const int st = it & 1;
+        mbar_wait(&do_full[st], (it >> 1) & 1);
         tc_fence_after();
-        // dP = dO · Vᵀ
+        const uint32_t do_base = smem_u32(sdO + st * Cfg::TILE);
 #pragma unroll
         for (int k = 0; k < C / 16; ++k) {
           const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
           umma_bf16_ss(tmem + Cfg::DP_COL, make_smem_desc(do_base + off, 16, 1024), make_smem_desc(v_base + off, 16, 1024), idesc_kk, k != 0);
         }
         umma_commit(dp_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_s(0);
+      issue_dp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const uint32_t ph = it & 1;
+        const int st = it & 1;
+        const uint32_t q_base = smem_u32(sQ + st * Cfg::TILE), do_base = smem_u32(sdO + st * Cfg::TILE);
         // dV += Pᵀ · dO        (A = P as MN-major [k = q rows][m = kv], B = dO as MN-major [k = q rows][n = c])
         mbar_wait(p_ready, ph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16_ss(tmem + Cfg::DV_COL, make_smem_desc(p_base + k * 2048, 128 * 128, 1024),
+          umma_bf16_ss(tmem + Cfg::DV_COL, make_smem_desc(ps_base + k * 2048, 128 * 128, 1024),
                        make_smem_desc(do_base + k * 2048, 128 * 128, 1024), idesc_mm, (it | k) != 0);
-        // dK += dSᵀ · Q ; dQ = dS · K
+        umma_commit(dv_done);
+        // dK += dSᵀ · Q ; dQ = dS · K   (dS overwrote P in the same buffer)
         mbar_wait(ds_ready, ph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16_ss(tmem + Cfg::DK_COL, make_smem_desc(ds_base + k * 2048, 128 * 128, 1024),
+          umma_bf16_ss(tmem + Cfg::DK_COL, make_smem_desc(ps_base + k * 2048, 128 * 128, 1024),
                        make_smem_desc(q_base + k * 2048, 128 * 128, 1024), idesc_mm, (it | k) != 0);
 #pragma unroll
         for (int k = 0; k < 128 / 16; ++k) {
           const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
-          umma_bf16_ss(tmem + Cfg::S_COL, make_smem_desc(ds_base + off, 16, 1024), make_smem_desc(k_base + k * 2048, 128 * 128, 1024), idesc_km, k != 0);
+          umma_bf16_ss(tmem + Cfg::DP_COL, make_smem_desc(ps_base + off, 16, 1024), make_smem_desc(k_base + k * 2048, 128 * 128, 1024), idesc_km, k != 0);
         }
-        umma_commit(qdo_empty);
+        umma_commit(&qdo_empty[st]);
         umma_commit(dq_full);
+        if (it + 1 < n_it) {
+          issue_s(it + 1);                       // S columns were released at p_ready(it)
+          mbar_wait(dq_drained, ph);             // dQ(it) read out -> dP columns reusable
+          tc_fence_after();
+          issue_dp(it + 1);
+        }
       }
     }
   } else {
-    // thread = query row inside the current query tile (and kv row in the final dK/dV epilogue)
-    const int row = threadIdx.x;
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    // ------------------------------- compute warps -------------------------------
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;             // query row inside the tile == TMEM lane
+    const int cbase = half * 64;                     // this thread's 64 key columns
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sl2 = scale * kLog2e;
+    const bool issuer = (threadIdx.x == 0);
     for (int it = 0; it < n_it; ++it) {
       const uint32_t ph = it & 1;
       const int q0 = (jt + it) * 128;
       const int q_idx = q0 + row;
       const bool qvalid = q_idx < T;
-      const long long sidx = (static_cast<long long>(b) * H + h) * T + q_idx;
-      const float lse2 = qvalid ? lse[sidx] * kLog2e : 0.f;
-      const float dlt = qvalid ? delta[sidx] : 0.f;
-      const bool diag = (it == 0);
-      if (it > 0) {
-        // P and dS buffers are free once the previous tile's dV/dK/dQ MMAs retired (dq_full) — waited below before reuse
-      }
+      const long long sidx = (static_cast<long long>(b) * H + h) * T + (qvalid ? q_idx : 0);
+      const float lse2 = lse[sidx] * kLog2e;
+      const float dsc = delta[sidx] * scale;
+      const bool masked = (it == 0) || (q0 + 128 > T) || (kv0 + 128 > T);
+      float p[64];
+      // ---- P = exp2(S*c - lse)
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // P = exp2(S*c - lse) -> smem
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t r[32];
-        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_x32(t_lane + Cfg::S_COL + cbase, r0);
+        tmem_ld_x32(t_lane + Cfg::S_COL + cbase + 32, r1);
         tmem_ld_wait();
-        float p[32];
+        if (!masked) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int kv = kv0 + ch * 32 + e;
-          float pe = exp2f(__uint_as_float(r[e]) * sl2 - lse2);
-          if (!qvalid || kv >= T || (diag && kv > q_idx)) pe = 0.f;
-          p[e] = pe;
-        }
+          for (int e = 0; e < 32; ++e) {
+            p[e] = exp2f(fmaf(__uint_as_float(r0[e]), sl2, -lse2));
+            p[32 + e] = exp2f(fmaf(__uint_as_float(r1[e]), sl2, -lse2));
+          }
+        } else {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v4 = make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
-                                pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7]));
-          st_swizzled_chunk(sP, 128, row, ch * 4 + g, v4);
+          for (int e = 0; e < 64; ++e) {
+            const int kv = kv0 + cbase + e;
+            const float sv = __uint_as_float(e < 32 ? r0[e & 31] : r1[e & 31]);
+            const bool dead = !qvalid || kv >= T || kv > q_idx;
+            p[e] = dead ? 0.f : exp2f(fmaf(sv, sl2, -lse2));
+          }
         }
       }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 v4 = make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
+                              pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7]));
+        st_swizzled_chunk(sPS, 128, row, half * 8 + g, v4);
+      }
+      tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(p_ready);
-      // dS = P ∘ (dP − δ) · scale -> smem   (P recomputed from S, which is still in TMEM)
+      // ---- dS = P ∘ (dP·scale − δ·scale)   (kept in registers until the dV MMA has finished reading P)
       mbar_wait(dp_full, ph);
       tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t r[32], d[32];
-        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
-        tmem_ld_x32(t_lane + Cfg::DP_COL + ch * 32, d);
+      {
+        uint32_t d0[32], d1[32];
+        tmem_ld_x32(t_lane + Cfg::DP_COL + cbase, d0);
+        tmem_ld_x32(t_lane + Cfg::DP_COL + cbase + 32, d1);
         tmem_ld_wait();
-        float ds[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const int kv = kv0 + ch * 32 + e;
-          float pe = exp2f(__uint_as_float(r[e]) * sl2 - lse2);
-          if (!qvalid || kv >= T || (diag && kv > q_idx)) pe = 0.f;
-          ds[e] = pe * (__uint_as_float(d[e]) - dlt) * scale;
+          p[e] *= fmaf(__uint_as_float(d0[e]), scale, -dsc);
+          p[32 + e] *= fmaf(__uint_as_float(d1[e]), scale, -dsc);
         }
+      }
+      mbar_wait(dv_done, ph);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v4 = make_uint4(pack_bf16(ds[8 * g], ds[8 * g + 1]), pack_bf16(ds[8 * g + 2], ds[8 * g + 3]),
-                                pack_bf16(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16(ds[8 * g + 6], ds[8 * g + 7]));
-          st_swizzled_chunk(sdS, 128, row, ch * 4 + g, v4);
-        }
+      for (int g = 0; g < 8; ++g) {
+        uint4 v4 = make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
+                              pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7]));
+        st_swizzled_chunk(sPS, 128, row, half * 8 + g, v4);
       }
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(ds_ready);
-      // drain dQ (aliases S): fp32 vector atomics into dq_accum
+      // ---- drain dQ (TMEM, aliasing dP) -> fp32 staging in the P/dS buffer -> TMA reduce-add into dq_accum
       mbar_wait(dq_full, ph);
       tc_fence_after();
-      float* dqrow = dq_accum + ((static_cast<long long>(b) * T + q_idx) * H + h) * C;
+      constexpr int ROUNDS = C / 64;               // every round moves 32 columns per column-half
+      uint32_t dq[ROUNDS][32];
 #pragma unroll
-      for (int ch = 0; ch < C / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
-        tmem_ld_wait();
-        if (qvalid) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            atomicAdd(reinterpret_cast<float4*>(dqrow + ch * 32 + g * 4),
-                      make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                                  __uint_as_float(r[4 * g + 3])));
-        }
-      }
+      for (int rd = 0; rd < ROUNDS; ++rd) tmem_ld_x32(t_lane + Cfg::DP_COL + half * (C / 2) + rd * 32, dq[rd]);
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(dq_drained);
+      mbar_arrive(dq_drained);                     // TMEM side is done; the MMA warp may issue dP(it+1)
+#pragma unroll
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        uint8_t* stg = sPS + half * (128 * 128) + row * 128;     // [128 rows x 128 B] box per column-half
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(stg + ((g ^ (row & 7)) << 4)) = make_uint4(dq[rd][4 * g], dq[rd][4 * g + 1], dq[rd][4 * g + 2], dq[rd][4 * g + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        if (issuer) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+            tma_reduce_add_3d(&tmdQ, sPS + hh * (128 * 128), h * C + hh * (C / 2) + rd * 32, q0, b);
+          tma_commit_group();
+          tma_wait_group_read<0>();
+        }
+        named_bar_sync(2, 256);                    // staging area reusable (next round / next tile's P)
+      }
     }
-    // epilogue: dV, dK (thread = kv row).  The last dq_full wait above also covers the final dV/dK MMAs.
+    // ---- epilogue: dV, dK (thread = kv row x column half).  The last dq_full wait also covers the final dV/dK MMAs.
     const int kv_idx = kv0 + row;
     const bool kvalid = kv_idx < T;
     const long long krow = kvalid ? (static_cast<long long>(b) * T + kv_idx) : 0;
-    __nv_bfloat16* dvrow = dv + krow * dkv_row_stride + static_cast<long long>(h) * C;
-    __nv_bfloat16* dkrow = dk + krow * dkv_row_stride + static_cast<long long>(h) * C;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* dst = which ? dkrow : dvrow;
-      const uint32_t col = which ? Cfg::DK_COL : Cfg::DV_COL;
+      __nv_bfloat16* dst = (which ? dk : dv) + krow * dkv_row_stride + static_cast<long long>(h) * C + half * (C / 2);
+      const uint32_t col = (which ? Cfg::DK_COL : Cfg::DV_COL) + half * (C / 2);
 #pragma unroll
-      for (int ch = 0; ch < C / 32; ++ch) {
+      for (int ch = 0; ch < C / 64; ++ch) {
         uint32_t r[32];
         tmem_ld_x32(t_lane + col + ch * 32, r);     // warp-collective: executed by every lane, stores are guarded
         tmem_ld_wait();
@@ -565,11 +651,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+    if (issuer) tma_wait_group<0>();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+  if (warp == 9) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
 // ================================================================================================
@@ -619,16 +706,17 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
   dim3 grid((T + 127) / 128, H, B);
   CUtensorMap tq = make_tmap_bthc(q, B, T, H, C, q_row_stride, 128), tk = make_tmap_bthc(k, B, T, H, C, k_row_stride, 128),
               tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, 128), tdo = make_tmap_bthc(dout, B, T, H, C, static_cast<long long>(H) * C, 128);
+  CUtensorMap tdq = make_tmap_dq(dq_accum, B, T, H * C);
   if (C == 64) {
     static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
     (void)once;
-    attn_bwd_kernel<64><<<grid, 192, BwdCfg<64>::SMEM, s>>>(tq, tk, tv, tdo, lse, delta, dq_accum, static_cast<__nv_bfloat16*>(dk),
-                                                             static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale);
+    attn_bwd_kernel<64><<<grid, BwdCfg<64>::THREADS, BwdCfg<64>::SMEM, s>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk),
+                                                                             static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale);
   } else if (C == 128) {
     static bool once = (set_smem(attn_bwd_kernel<128>, BwdCfg<128>::SMEM), true);
     (void)once;
-    attn_bwd_kernel<128><<<grid, 192, BwdCfg<128>::SMEM, s>>>(tq, tk, tv, tdo, lse, delta, dq_accum, static_cast<__nv_bfloat16*>(dk),
-                                                               static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale);
+    attn_bwd_kernel<128><<<grid, BwdCfg<128>::THREADS, BwdCfg<128>::SMEM, s>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk),
+                                                                               static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale);
   } else {
     throw std::runtime_error("attention: head_dim must be 64 or 128");
   }

@@ -8,10 +8,12 @@
 //   dgrad     dx = dy · W           A K-major,  B MN-major  (· gelu'(pre) for the MLP up-projection)
 //   wgrad     dW += dyᵀ · x         A MN-major, B MN-major  fp32 output, TMA reduce-add accumulation
 //
-// Roles (192 threads, 1 CTA / SM, grid = #SMs, static persistent tile schedule with M-grouping for L2 reuse):
+// Roles (320 threads, 1 CTA / SM, grid = #SMs, static persistent tile schedule with M-grouping for L2 reuse):
 //   warp 0   TMA producer   (one elected lane)
 //   warp 1   TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warp 2-5 epilogue: TMEM -> registers -> epilogue math -> smem staging -> TMA store / reduce-add
+//   warp 2-9 epilogue: TMEM -> registers -> epilogue math -> smem staging -> TMA store / reduce-add.
+//            Two warps share each TMEM lane quarter and split every column chunk in half, so each SM
+//            sub-partition has two epilogue warps to hide tcgen05.ld / MUFU latency behind each other.
 // Pipelines: smem ring (full/empty mbarriers, 4 stages of 128x64 A + 256x64 B), TMEM ring (2 x 256 columns).
 #include "common.cuh"
 
@@ -30,8 +32,8 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int CSTAGE_BYTES = BM * 128;                 // 128 rows x 128 B (64 bf16 or 32 fp32 per row)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 256 + 1024;  // + barriers + align slack
 constexpr int GROUP_M = 8;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;     // 2 control warps + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
 
 enum Epilogue : int {
   EPI_STORE = 0,      // D = acc                       (bf16)
@@ -165,6 +167,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which half of every column chunk this warp handles
     const int row = q * 32 + lane;                // row inside the 128-row tile
     const bool issuer = (threadIdx.x == 64);      // first epilogue thread issues the TMA stores
     const uint32_t sw = (row & 7);
@@ -180,20 +183,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const long long grow = static_cast<long long>(m_blk) * BM + row;
 
       if (EPI == EPI_F32) {
-        // 8 chunks of 32 fp32 columns (128 B per row)
+        // 8 chunks of 32 fp32 columns (128 B per row); each warp of a pair moves 16 of them
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint8_t* sbuf = sC + (c & 1) * CSTAGE_BYTES;
           if (issuer) tma_wait_group_read<1>();
           named_bar_sync(1, EPI_THREADS);
-          uint32_t r[32];
-          tmem_ld_x32(t_row + c * 32, r);
+          uint32_t r[16];
+          tmem_ld_x16(t_row + c * 32 + half * 16, r);
           tmem_ld_wait();
           uint8_t* rowp = sbuf + row * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = v;
+            *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = v;
           }
           fence_proxy_async_smem();
           named_bar_sync(2, EPI_THREADS);
@@ -207,7 +210,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       } else {
-        // 4 chunks of 64 bf16 columns (128 B per row)
+        // 4 chunks of 64 bf16 columns (128 B per row); each warp of a pair converts 32 of them
 #pragma unroll 1
         for (int c = 0; c < BN / 64; ++c) {
           uint8_t* sbuf = (EPI == EPI_GELU) ? sC : sC + (c & 1) * CSTAGE_BYTES;
@@ -217,21 +220,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             else tma_wait_group_read<1>();
           }
           named_bar_sync(1, EPI_THREADS);
-          uint32_t r[64];
-          {
-            uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-            uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-            tmem_ld_x32(t_row + c * 64, r0);
-            tmem_ld_x32(t_row + c * 64 + 32, r1);
-            tmem_ld_wait();
-          }
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c * 64 + half * 32, r);
+          tmem_ld_wait();
           const int col0 = n_blk * BN + c * 64;
           const bool valid = (grow < p.M) && (col0 < p.N);
           uint8_t* rowp = sbuf + row * 128;
           if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + grow * p.ld_aux + col0);
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + grow * p.ld_aux + col0) + half * 4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               uint4 a = valid ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
               uint32_t au[4] = {a.x, a.y, a.z, a.w};
               uint32_t o[4];
@@ -243,12 +241,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 else { x0 *= gelu_tanh_grad(av.x); x1 *= gelu_tanh_grad(av.y); }
                 o[e] = pack_bf16(x0, x1);
               }
-              *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           } else {
             uint8_t* rowp2 = sbuf2 + row * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               uint32_t o[4], g[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -260,8 +258,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   g[e] = pack_bf16(gelu_tanh(xr.x), gelu_tanh(xr.y));
                 }
               }
-              *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-              if (EPI == EPI_GELU) *reinterpret_cast<uint4*>(rowp2 + ((j ^ sw) << 4)) = make_uint4(g[0], g[1], g[2], g[3]);
+              *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              if (EPI == EPI_GELU) *reinterpret_cast<uint4*>(rowp2 + (((half * 4 + j) ^ sw) << 4)) = make_uint4(g[0], g[1], g[2], g[3]);
             }
           }
           fence_proxy_async_smem();
