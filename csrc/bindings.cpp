@@ -8,6 +8,10 @@ namespace mg {
 void gemm_launch(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d, long long ldd,
                  void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int accumulate,
                  int num_sms, cudaStream_t stream);
+void gemm_launch_ag_raw(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, void* d2, long long ldd2,
+                        const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms, cudaStream_t stream,
+                        const long long* peer_ptrs, void* local, unsigned int* flags, long long chunk_elems, long long b_offset,
+                        unsigned int target, int world, int rank, int n_ctas);
 void rmsnorm_fwd(const void* x, void* y, float* rstd, int M, int D, float eps, cudaStream_t s);
 void rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* dres, void* dx, int M, int D, cudaStream_t s);
 void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const float* sin_t, const float* cos_t, void* qk,
@@ -81,6 +85,30 @@ void gemm(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn, at::Te
   mg::gemm_launch(a.data_ptr(), a.stride(0), a_mn, b.data_ptr(), b.stride(0), b_mn, d.data_ptr(), d.stride(0), d2p, ldd2, auxp,
                   ld_aux, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), accumulate ? 1 : 0,
                   num_sms_of(a), stream());
+}
+
+// all-gather ⊕ GEMM: d = a · bᵀ where b ([N,K], K-major) is a sub-range of the local gathered unit buffer `local`, whose
+// remote chunks are pulled from `peer_ptrs` by the first n_ctas CTAs of the same kernel (csrc/gemm.cu).
+void gemm_ag(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, int64_t epi, const c10::optional<at::Tensor>& d2,
+             const c10::optional<at::Tensor>& aux, std::vector<int64_t> peer_ptrs, at::Tensor& local, at::Tensor& flags,
+             int64_t chunk_elems, int64_t target, int64_t rank, int64_t n_ctas) {
+  c10::cuda::CUDAGuard guard(a.device());
+  CHECK_BF16(a); CHECK_BF16(b); CHECK_BF16(d); CHECK_BF16(local); CHECK_2D_ROWMAJOR(a); CHECK_2D_ROWMAJOR(b); CHECK_2D_ROWMAJOR(d);
+  TORCH_CHECK(b.is_contiguous() && local.is_contiguous() && flags.scalar_type() == at::kInt);
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K && d.size(0) == M && d.size(1) == N);
+  const int64_t b_offset = (reinterpret_cast<const char*>(b.data_ptr()) - reinterpret_cast<const char*>(local.data_ptr())) / 2;
+  TORCH_CHECK(b_offset >= 0 && b_offset + N * K <= local.numel(), "gemm_ag: b must live inside the local unit buffer");
+  TORCH_CHECK(chunk_elems % 8 == 0 && static_cast<int64_t>(peer_ptrs.size()) * chunk_elems <= local.numel());
+  const void* auxp = nullptr; long long ld_aux = 0;
+  if (epi == 1 || epi == 3) { TORCH_CHECK(aux.has_value()); CHECK_BF16(*aux); auxp = aux->data_ptr(); ld_aux = aux->stride(0); }
+  void* d2p = nullptr; long long ldd2 = 0;
+  if (epi == 2) { TORCH_CHECK(d2.has_value()); CHECK_BF16(*d2); d2p = d2->data_ptr(); ldd2 = d2->stride(0); }
+  std::vector<long long> pp(peer_ptrs.begin(), peer_ptrs.end());
+  mg::gemm_launch_ag_raw(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), d.data_ptr(), d.stride(0), d2p, ldd2, auxp, ld_aux,
+                         static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), num_sms_of(a), stream(),
+                         pp.data(), local.data_ptr(), reinterpret_cast<unsigned int*>(flags.data_ptr()), chunk_elems, b_offset,
+                         static_cast<unsigned int>(target), static_cast<int>(pp.size()), static_cast<int>(rank), static_cast<int>(n_ctas));
 }
 
 std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, double eps) {
@@ -242,6 +270,7 @@ void ag_pull(std::vector<int64_t> lp_ptrs, at::Tensor& local, int64_t shard_elem
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM with fused epilogues");
+  m.def("gemm_ag", &gemm_ag, "all-gather (NVLink pull) fused with the tcgen05 GEMM");
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("qkln_rope_fwd", &qkln_rope_fwd);

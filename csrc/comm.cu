@@ -149,13 +149,22 @@ __global__ void __launch_bounds__(512) ag_pull_kernel(PeerPtrs lp, __nv_bfloat16
                                                       uint32_t* __restrict__ flags) {
   for (int k = 1; k < world; ++k) {
     const int c = (rank + k) % world;
-    const uint4* src = reinterpret_cast<const uint4*>(lp.p[c]) + static_cast<long long>(c) * shard16;
+    const uint4* src = reinterpret_cast<const uint4*>(lp.p[c]);          // peer c's shard of this unit
     uint4* dst = reinterpret_cast<uint4*>(local) + static_cast<long long>(c) * shard16;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < shard16;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-      uint4 v;
-      asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
-      dst[i] = v;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < shard16; i0 += stride * 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < shard16)
+          asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + i));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < shard16) dst[i] = v[u];
+      }
     }
     __threadfence();
     __syncthreads();

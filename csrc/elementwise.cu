@@ -148,123 +148,135 @@ void rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* d
 // (EPL even => RoPE pairs never straddle lanes).  sin/cos come from a [T, C/2] fp32 table.
 // Input  qkv  [M, 3, H, C] bf16 (raw projection);  output qk [M, 2, H, C] bf16;  stats [M, 2, H, 2] fp32.
 // ------------------------------------------------------------------------------------------------
-template <int EPL>
+// (QK-LayerNorm + RoPE kernels)
+// Each vector (one head of q or k for one token, C elements) is handled by LPV = C/8 lanes, 8 elements (16 B) per
+// lane, so a warp processes 32/LPV vectors per pass with 16-byte loads/stores; reductions are sub-warp shuffles.
+template <int LPV>
+MG_DEVICE float group_sum(float v) {
+#pragma unroll
+  for (int o = LPV / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+MG_DEVICE void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+MG_DEVICE uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+template <int C>
 __global__ void __launch_bounds__(256) qkln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ q_gain,
                                                             const float* __restrict__ k_gain, const float* __restrict__ sin_t,
                                                             const float* __restrict__ cos_t, __nv_bfloat16* __restrict__ qk,
                                                             float* __restrict__ stats, long long nvec, int T, int H, float eps) {
-  constexpr int C = EPL * 32;
-  const long long vec = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (vec >= nvec) return;
-  const int h = vec % H;
-  const int which = (vec / H) & 1;          // 0 = q, 1 = k
-  const long long m = vec / (2 * H);
-  const int pos = m % T;
-  const __nv_bfloat16* src = qkv + (m * 3 + which) * H * C + static_cast<long long>(h) * C + lane * EPL;
-  float v[EPL];
-  if (EPL == 2) {
-    float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(src));
-    v[0] = f.x; v[1] = f.y;
-  } else {
-    uint2 u = *reinterpret_cast<const uint2*>(src);
-    float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
-    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
-  }
-  float s = 0.f;
+  constexpr int LPV = C / 8, VPW = 32 / LPV;
+  const int lane = threadIdx.x & 31, sub = lane % LPV, slot = lane / LPV;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int c0 = sub * 8;
+  float gq[8], gk[8];
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) s += v[e];
-  const float mu = warp_sum(s) / C;
-  float ss = 0.f;
+  for (int e = 0; e < 8; ++e) { gq[e] = q_gain[c0 + e]; gk[e] = k_gain[c0 + e]; }
+  for (long long base = warp0 * VPW; base < nvec; base += nwarps * VPW) {
+    const long long vec = base + slot;
+    const bool ok = vec < nvec;
+    const long long v = ok ? vec : nvec - 1;
+    const int h = v % H;
+    const int which = (v / H) & 1;          // 0 = q, 1 = k
+    const long long m = v / (2 * H);
+    const int pos = m % T;
+    float x[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + (m * 3 + which) * H * C + static_cast<long long>(h) * C + c0)), x);
+    float s = 0.f;
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) { v[e] -= mu; ss += v[e] * v[e]; }
-  const float rs = rsqrtf(warp_sum(ss) / C + eps);
-  const float* gain = which ? k_gain : q_gain;
-  float o[EPL];
+    for (int e = 0; e < 8; ++e) s += x[e];
+    const float mu = group_sum<LPV>(s) / C;
+    float ss = 0.f;
 #pragma unroll
-  for (int e = 0; e < EPL; e += 2) {
-    const int c = lane * EPL + e;
-    const float a = v[e] * rs * gain[c], b = v[e + 1] * rs * gain[c + 1];
-    const float sn = sin_t[pos * (C / 2) + c / 2], cs = cos_t[pos * (C / 2) + c / 2];
-    o[e] = a * cs - b * sn;
-    o[e + 1] = b * cs + a * sn;
-  }
-  __nv_bfloat16* dst = qk + (m * 2 + which) * H * C + static_cast<long long>(h) * C + lane * EPL;
-  if (EPL == 2) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(o[0], o[1]);
-  else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
-  if (lane == 0) {
-    stats[vec * 2] = mu;
-    stats[vec * 2 + 1] = rs;
+    for (int e = 0; e < 8; ++e) { x[e] -= mu; ss += x[e] * x[e]; }
+    const float rs = rsqrtf(group_sum<LPV>(ss) / C + eps);
+    const float4 sn = __ldg(reinterpret_cast<const float4*>(sin_t + pos * (C / 2) + c0 / 2));
+    const float4 cs = __ldg(reinterpret_cast<const float4*>(cos_t + pos * (C / 2) + c0 / 2));
+    const float sv[4] = {sn.x, sn.y, sn.z, sn.w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      const float a = x[e] * rs * (which ? gk[e] : gq[e]), b = x[e + 1] * rs * (which ? gk[e + 1] : gq[e + 1]);
+      o[e] = a * cv[e / 2] - b * sv[e / 2];
+      o[e + 1] = b * cv[e / 2] + a * sv[e / 2];
+    }
+    if (ok) {
+      *reinterpret_cast<uint4*>(qk + (m * 2 + which) * H * C + static_cast<long long>(h) * C + c0) = pack8(o);
+      if (sub == 0) *reinterpret_cast<float2*>(stats + vec * 2) = make_float2(mu, rs);
+    }
   }
 }
 
 // In place on dqkv [M, 3, H, C] (q and k thirds): d(roped, normalised) -> d(raw projection output).
-// Gain gradients are accumulated per lane over a grid-stride loop, reduced through shared memory, then atomically added.
-template <int EPL>
+// Gain gradients are accumulated per lane over the grid-stride loop, reduced through shared memory, then atomically added.
+template <int C>
 __global__ void __launch_bounds__(256) qkln_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, const __nv_bfloat16* __restrict__ qkv_raw,
                                                             const float* __restrict__ stats, const float* __restrict__ q_gain,
                                                             const float* __restrict__ k_gain, const float* __restrict__ sin_t,
                                                             const float* __restrict__ cos_t, float* __restrict__ dq_gain,
                                                             float* __restrict__ dk_gain, long long nvec, int T, int H) {
-  constexpr int C = EPL * 32;
+  constexpr int LPV = C / 8, VPW = 32 / LPV;
   __shared__ float red[2][C];
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) (&red[0][0])[i] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, sub = lane % LPV, slot = lane / LPV;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  float gacc[2][EPL];
+  const int c0 = sub * 8;
+  float gq[8], gk[8], gacc[2][8];
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) gacc[0][e] = gacc[1][e] = 0.f;
-  for (long long vec = warp0; vec < nvec; vec += nwarps) {
-    const int h = vec % H;
-    const int which = (vec / H) & 1;
-    const long long m = vec / (2 * H);
+  for (int e = 0; e < 8; ++e) { gq[e] = q_gain[c0 + e]; gk[e] = k_gain[c0 + e]; gacc[0][e] = gacc[1][e] = 0.f; }
+  for (long long base = warp0 * VPW; base < nvec; base += nwarps * VPW) {
+    const long long vec = base + slot;
+    const bool ok = vec < nvec;
+    const long long v = ok ? vec : nvec - 1;
+    const int h = v % H;
+    const int which = (v / H) & 1;
+    const long long m = v / (2 * H);
     const int pos = m % T;
-    const long long off = (m * 3 + which) * H * C + static_cast<long long>(h) * C + lane * EPL;
-    float g[EPL], x[EPL];
-    if (EPL == 2) {
-      float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(dqkv + off));
-      float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(qkv_raw + off));
-      g[0] = a.x; g[1] = a.y; x[0] = b.x; x[1] = b.y;
-    } else {
-      uint2 a = *reinterpret_cast<const uint2*>(dqkv + off);
-      uint2 b = *reinterpret_cast<const uint2*>(qkv_raw + off);
-      float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y);
-      g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y;
-      x[0] = b0.x; x[1] = b0.y; x[2] = b1.x; x[3] = b1.y;
-    }
-    const float mu = stats[vec * 2], rs = stats[vec * 2 + 1];
-    const float* gain = which ? k_gain : q_gain;
-    float dxh[EPL], xh[EPL];
+    const long long off = (m * 3 + which) * H * C + static_cast<long long>(h) * C + c0;
+    float g[8], x[8];
+    unpack8(*reinterpret_cast<const uint4*>(dqkv + off), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv_raw + off)), x);
+    const float2 st = __ldg(reinterpret_cast<const float2*>(stats + v * 2));
+    const float mu = st.x, rs = st.y;
+    const float4 sn = __ldg(reinterpret_cast<const float4*>(sin_t + pos * (C / 2) + c0 / 2));
+    const float4 cs = __ldg(reinterpret_cast<const float4*>(cos_t + pos * (C / 2) + c0 / 2));
+    const float sv[4] = {sn.x, sn.y, sn.z, sn.w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
+    float dxh[8], xh[8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int e = 0; e < EPL; e += 2) {
-      const int c = lane * EPL + e;
-      const float sn = sin_t[pos * (C / 2) + c / 2], cs = cos_t[pos * (C / 2) + c / 2];
-      const float dn0 = g[e] * cs + g[e + 1] * sn;        // inverse rotation
-      const float dn1 = g[e + 1] * cs - g[e] * sn;
+    for (int e = 0; e < 8; e += 2) {
+      const float dn0 = g[e] * cv[e / 2] + g[e + 1] * sv[e / 2];        // inverse rotation
+      const float dn1 = g[e + 1] * cv[e / 2] - g[e] * sv[e / 2];
       xh[e] = (x[e] - mu) * rs;
       xh[e + 1] = (x[e + 1] - mu) * rs;
-      gacc[which][e] += dn0 * xh[e];
-      gacc[which][e + 1] += dn1 * xh[e + 1];
-      dxh[e] = dn0 * gain[c];
-      dxh[e + 1] = dn1 * gain[c + 1];
+      if (ok) {
+        if (which) { gacc[1][e] += dn0 * xh[e]; gacc[1][e + 1] += dn1 * xh[e + 1]; }
+        else { gacc[0][e] += dn0 * xh[e]; gacc[0][e + 1] += dn1 * xh[e + 1]; }
+      }
+      dxh[e] = dn0 * (which ? gk[e] : gq[e]);
+      dxh[e + 1] = dn1 * (which ? gk[e + 1] : gq[e + 1]);
       s1 += dxh[e] + dxh[e + 1];
       s2 += dxh[e] * xh[e] + dxh[e + 1] * xh[e + 1];
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
-    float o[EPL];
+    s1 = group_sum<LPV>(s1) / C;
+    s2 = group_sum<LPV>(s2) / C;
+    float o[8];
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) o[e] = rs * (dxh[e] - s1 - xh[e] * s2);
-    if (EPL == 2) *reinterpret_cast<uint32_t*>(dqkv + off) = pack_bf16(o[0], o[1]);
-    else *reinterpret_cast<uint2*>(dqkv + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    for (int e = 0; e < 8; ++e) o[e] = rs * (dxh[e] - s1 - xh[e] * s2);
+    if (ok) *reinterpret_cast<uint4*>(dqkv + off) = pack8(o);
   }
 #pragma unroll
   for (int w = 0; w < 2; ++w)
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) atomicAdd(&red[w][lane * EPL + e], gacc[w][e]);
+    for (int e = 0; e < 8; ++e) atomicAdd(&red[w][c0 + e], gacc[w][e]);
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     atomicAdd(dq_gain + i, red[0][i]);
@@ -275,11 +287,14 @@ __global__ void __launch_bounds__(256) qkln_rope_bwd_kernel(__nv_bfloat16* __res
 void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const float* sin_t, const float* cos_t, void* qk,
                    float* stats, long long M, int T, int H, int C, float eps, cudaStream_t s) {
   const long long nvec = M * 2 * H;
-  const unsigned grid = static_cast<unsigned>((nvec + 7) / 8);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = static_cast<unsigned>(sms * 8);
   if (C == 64)
-    qkln_rope_fwd_kernel<2><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
+    qkln_rope_fwd_kernel<64><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
   else if (C == 128)
-    qkln_rope_fwd_kernel<4><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
+    qkln_rope_fwd_kernel<128><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
   else throw std::runtime_error("qkln_rope: head_dim must be 64 or 128");
   check_launch("qkln_rope_fwd");
 }
@@ -288,9 +303,9 @@ void qkln_rope_bwd(void* dqkv, const void* qkv_raw, const float* stats, const fl
   const long long nvec = M * 2 * H;
   const unsigned grid = static_cast<unsigned>(num_sms * 8);
   if (C == 64)
-    qkln_rope_bwd_kernel<2><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
+    qkln_rope_bwd_kernel<64><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
   else if (C == 128)
-    qkln_rope_bwd_kernel<4><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
+    qkln_rope_bwd_kernel<128><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
   else throw std::runtime_error("qkln_rope: head_dim must be 64 or 128");
   check_launch("qkln_rope_bwd");
 }

@@ -43,12 +43,33 @@ enum Epilogue : int {
   EPI_F32 = 4,        // D (+)= acc                    (fp32; accumulate via TMA reduce-add)
 };
 
+// Optional fused all-gather (all-gather ⊕ GEMM): the B operand lives inside a flat FSDP unit
+// buffer whose world equal chunks are owned by different ranks.  The first `n_ctas` CTAs first PULL the peers'
+// chunks over NVLink into the local buffer and publish one ready flag per chunk; every CTA's TMA producer polls
+// the flags of the chunks its B tile touches, and tiles are visited so that locally-owned rows come first.
+struct GatherParams {
+  void* peer[8];                    // peer[c] = rank c's bf16 shard (symmetric memory), length chunk_elems
+  __nv_bfloat16* local;             // local gathered unit buffer, world * chunk_elems elements
+  unsigned int* flags;              // one counter per chunk; chunk c is complete when flags[c] == target
+  long long chunk_elems;            // elements per chunk (multiple of 8)
+  long long b_offset;               // element offset of the B matrix inside the unit buffer
+  unsigned int target;
+  int world, rank, n_ctas;
+};
+
 struct GemmParams {
   const __nv_bfloat16* aux;
   long long ld_aux;
   int M, N, K;
   int accumulate;
+  GatherParams ag;
 };
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -91,6 +112,41 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // ---- fused all-gather: producer CTAs pull the peers' chunks (ring order starting after the local chunk)
+  const bool gather = p.ag.n_ctas > 0;
+  if (gather && static_cast<int>(blockIdx.x) < p.ag.n_ctas) {
+    const long long n16 = p.ag.chunk_elems >> 3;
+    for (int k = 1; k < p.ag.world; ++k) {
+      const int c = (p.ag.rank + k) % p.ag.world;
+      const uint4* src = reinterpret_cast<const uint4*>(p.ag.peer[c]);
+      uint4* dst = reinterpret_cast<uint4*>(p.ag.local + static_cast<long long>(c) * p.ag.chunk_elems);
+      // 8 independent 16-byte NVLink loads in flight per thread (peer latency is ~2 us; bandwidth needs depth)
+      const long long stride = static_cast<long long>(p.ag.n_ctas) * blockDim.x;
+      for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n16; i0 += stride * 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < n16)
+            asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + i));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < n16) dst[i] = v[u];
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // the data is consumed by TMA (async proxy)
+        atomicAdd(p.ag.flags + c, 1u);
+      }
+    }
+  }
+
+  // tile -> (m_blk, n_blk).  With a fused gather the n-blocks are rotated so that locally-owned weight rows come first.
+  const int n_rot = gather ? static_cast<int>(((static_cast<long long>(p.ag.rank) * p.ag.chunk_elems - p.ag.b_offset) / p.K) / BN) : 0;
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
     const int per_group = GROUP_M * num_n;
     const int g = tile / per_group;
@@ -99,6 +155,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int r = tile - g * per_group;
     m_blk = first_m + r % gsize;
     n_blk = r / gsize;
+    if (gather) {
+      int rot = n_rot < 0 ? 0 : (n_rot >= num_n ? 0 : n_rot);
+      n_blk = (n_blk + rot) % num_n;
+    }
   };
 
   if (warp == 0) {
@@ -109,6 +169,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
+        if (gather) {
+          const long long e0 = p.ag.b_offset + static_cast<long long>(n_blk) * BN * p.K;
+          const long long rows = min(BN, p.N - n_blk * BN);
+          const long long e1 = e0 + rows * p.K - 1;
+          const int c0 = static_cast<int>(e0 / p.ag.chunk_elems), c1 = static_cast<int>(e1 / p.ag.chunk_elems);
+          for (int c = c0; c <= c1 && c < p.ag.world; ++c) {
+            if (c == p.ag.rank) continue;
+            while (ld_acquire_gpu_u32(p.ag.flags + c) < p.ag.target) {
+            }
+          }
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -342,7 +414,8 @@ static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     configured = true;
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  if (p.ag.n_ctas > grid) grid = p.ag.n_ctas < num_sms ? p.ag.n_ctas : num_sms;
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tA, tB, tD, tD2, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("gemm launch: ") + cudaGetErrorString(e));
@@ -350,14 +423,42 @@ static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 
 // a: [M,K] row-major (a_mn=0) or [K,M] row-major (a_mn=1);  b: [N,K] (b_mn=0) or [K,N] (b_mn=1)
 // d: [M,N] bf16 (fp32 for EPI_F32); d2: second bf16 output for EPI_GELU; aux: [M,N] bf16 for RESIDUAL / DGELU.
+void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d,
+                    long long ldd, void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K,
+                    int epi, int accumulate, int num_sms, cudaStream_t stream, const GatherParams* ag);
+
 void gemm_launch(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d,
                  long long ldd, void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K,
                  int epi, int accumulate, int num_sms, cudaStream_t stream) {
+  gemm_launch_ag(a, lda, a_mn, b, ldb, b_mn, d, ldd, d2, ldd2, aux, ld_aux, M, N, K, epi, accumulate, num_sms, stream, nullptr);
+}
+
+// Host entry for all-gather ⊕ GEMM: same as gemm_launch plus the gather description (b must be K-major and be the
+// sub-range [b_offset, b_offset + N*K) of the local unit buffer).
+void gemm_launch_ag_raw(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, void* d2, long long ldd2,
+                        const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms, cudaStream_t stream,
+                        const long long* peer_ptrs, void* local, unsigned int* flags, long long chunk_elems, long long b_offset,
+                        unsigned int target, int world, int rank, int n_ctas) {
+  GatherParams ag{};
+  for (int i = 0; i < 8; ++i) ag.peer[i] = i < world ? reinterpret_cast<void*>(peer_ptrs[i]) : nullptr;
+  ag.local = static_cast<__nv_bfloat16*>(local);
+  ag.flags = flags; ag.chunk_elems = chunk_elems; ag.b_offset = b_offset; ag.target = target;
+  ag.world = world; ag.rank = rank; ag.n_ctas = n_ctas;
+  gemm_launch_ag(a, lda, false, b, ldb, false, d, ldd, d2, ldd2, aux, ld_aux, M, N, K, epi, 0, num_sms, stream, &ag);
+}
+
+void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d,
+                    long long ldd, void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K,
+                    int epi, int accumulate, int num_sms, cudaStream_t stream, const GatherParams* ag) {
   CUtensorMap tA = a_mn ? make_tmap_2d(a, 2, K, M, lda, 64, BK) : make_tmap_2d(a, 2, M, K, lda, BK, BM);
   CUtensorMap tB = b_mn ? make_tmap_2d(b, 2, K, N, ldb, 64, BK) : make_tmap_2d(b, 2, N, K, ldb, BK, BN);
   CUtensorMap tD = (epi == EPI_F32) ? make_tmap_2d(d, 4, M, N, ldd, 32, BM) : make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
-  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate};
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}};
+  if (ag) {
+    p.ag = *ag;
+    if (a_mn || b_mn) throw std::runtime_error("all-gather ⊕ GEMM needs K-major operands");
+  }
 #define MG_CASE(AM, BM_, E) \
   if (a_mn == AM && b_mn == BM_ && epi == E) return launch_one<AM, BM_, E>(tA, tB, tD, tD2, p, num_sms, stream);
   MG_CASE(false, false, EPI_STORE)

@@ -80,7 +80,7 @@ class GPTModel:
         with self._range("block"):
             h1, rstd1 = be.rmsnorm_fwd(x, 1e-6)
             with self._range("causal_sa"):
-                qkv_raw = be.linear_fwd(h1, w["c_attn"])
+                qkv_raw = be.linear_fwd(h1, w["c_attn"], gather=w.get("__gather__"))
                 qkv, stats = be.qkln_rope_fwd(qkv_raw, w["q_ln"], w["k_ln"], B, T, H, C)
                 o, lse = be.attention_fwd(qkv, B, T, H, C, p, _site_seed(step_seed, micro, layer, 1))
                 if p == 0.0:
@@ -151,7 +151,7 @@ class GPTModel:
             # final norm + fused LM head / CE (forward and backward in one pass)
             wh = wp.acquire(L + 1)
             hf, rstdf = be.rmsnorm_fwd(x, 1e-5)
-            loss_sum, dhf = be.lmhead_ce(hf, wh["lm_head"], targets, wp.grads(L + 1)["lm_head"], grad_scale)
+            loss_sum, dhf = be.lmhead_ce(hf, wh["lm_head"], targets, wp.grads(L + 1)["lm_head"], grad_scale, gather=wh.get("__gather__"))
             wp.release(L + 1)
             wp.grads_ready(L + 1)
             dx = be.rmsnorm_bwd(dhf, x, rstdf)
@@ -193,7 +193,7 @@ class GPTModel:
         hf = self.forward_hidden(wp, idx)
         L = self.cfg.n_layer
         wh = wp.acquire(L + 1)
-        loss_sum, _ = self.be.lmhead_ce(hf, wh["lm_head"], targets, None, 0.0)
+        loss_sum, _ = self.be.lmhead_ce(hf, wh["lm_head"], targets, None, 0.0, gather=wh.get("__gather__"))
         wp.release(L + 1)
         return loss_sum / idx.numel()
 
@@ -206,6 +206,6 @@ class GPTModel:
         if positions is not None:
             rows = torch.arange(B, device=idx.device) * T + positions.to(idx.device)
             hf = hf[rows]
-        logits = self.be.lmhead_logits(hf, wh["lm_head"])
+        logits = self.be.lmhead_logits(hf, wh["lm_head"], gather=wh.get("__gather__"))
         wp.release(L + 1)
         return logits if positions is not None else logits.view(B, T, -1)

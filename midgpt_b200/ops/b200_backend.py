@@ -61,8 +61,15 @@ class B200Backend:
         self.launches = 0          # kernels launched through this backend (bench.py reports it)
 
     # ---------------------------------------------------------------- helpers
-    def _gemm(self, a, a_mn, b, b_mn, d, epi=EPI_STORE, d2=None, aux=None, accumulate=False):
-        self.ext.gemm(a, a_mn, b, b_mn, d, epi, d2, aux, accumulate)
+    def _gemm(self, a, a_mn, b, b_mn, d, epi=EPI_STORE, d2=None, aux=None, accumulate=False, gather=None):
+        if gather is not None:
+            # all-gather ⊕ GEMM: the weight's unit is still being pulled from the peers by the first CTAs of this very kernel
+            assert not a_mn and not b_mn and not accumulate
+            self.ext.gemm_ag(a, b, d, epi, d2, aux, gather.peer_ptrs, gather.local, gather.flags, gather.chunk_elems,
+                             gather.target, gather.rank, gather.n_ctas)
+            gather.done = True
+        else:
+            self.ext.gemm(a, a_mn, b, b_mn, d, epi, d2, aux, accumulate)
         self.launches += 1
 
     def _rope_tables(self, C: int, T: int):
@@ -100,17 +107,19 @@ class B200Backend:
         return self.ext.rmsnorm_bwd(dy, x, rstd, dres)
 
     # ---------------------------------------------------------------- linear
-    def linear_fwd(self, x, w, res=None, act=None):
+    def linear_fwd(self, x, w, res=None, act=None, gather=None):
         M, N = x.shape[0], w.shape[0]
         y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+        if gather is not None and gather.done:
+            gather = None
         if act == "gelu":
             a = torch.empty_like(y)
-            self._gemm(x, False, w, False, y, EPI_GELU, d2=a)
+            self._gemm(x, False, w, False, y, EPI_GELU, d2=a, gather=gather)
             return y, a
         if res is not None:
-            self._gemm(x, False, w, False, y, EPI_RESIDUAL, aux=res)
+            self._gemm(x, False, w, False, y, EPI_RESIDUAL, aux=res, gather=gather)
         else:
-            self._gemm(x, False, w, False, y, EPI_STORE)
+            self._gemm(x, False, w, False, y, EPI_STORE, gather=gather)
         return y
 
     def linear_dgrad(self, dy, w, gelu_pre=None, dres=None):
@@ -172,14 +181,14 @@ class B200Backend:
             self._logits_ws = torch.empty(need, dtype=torch.bfloat16, device=self.device)
         return self._logits_ws[:need].view(rows, vpad)
 
-    def lmhead_logits(self, h, w):
+    def lmhead_logits(self, h, w, gather=None):
         V = w.shape[0]
         vpad = (V + 7) // 8 * 8
         buf = torch.empty((h.shape[0], vpad), dtype=torch.bfloat16, device=h.device)
-        self._gemm(h, False, w, False, buf[:, :V], EPI_STORE)
+        self._gemm(h, False, w, False, buf[:, :V], EPI_STORE, gather=gather)
         return buf[:, :V]
 
-    def lmhead_ce(self, h, w, targets, dw_acc=None, grad_scale: float = 0.0, chunk: int = 8192):
+    def lmhead_ce(self, h, w, targets, dw_acc=None, grad_scale: float = 0.0, chunk: int = 8192, gather=None):
         M, V = h.shape[0], w.shape[0]
         vpad = (V + 7) // 8 * 8
         tg = targets.reshape(-1).to(torch.int32).contiguous()
@@ -190,7 +199,7 @@ class B200Backend:
             buf = self._logits_buf(e - s, vpad)
             logits = buf[:, :V]
             hc = h[s:e]
-            self._gemm(hc, False, w, False, logits, EPI_STORE)
+            self._gemm(hc, False, w, False, logits, EPI_STORE, gather=gather if s == 0 else None)
             self.ext.ce_chunk(buf, tg[s:e], loss_sum, V, float(grad_scale), dw_acc is not None)
             self.launches += 1
             if dw_acc is not None:

@@ -83,7 +83,7 @@ class TorchBackend:
         return dx.to(x.dtype)
 
     # ---------------------------------------------------------------- linear (K3,K7,K8,K9)
-    def linear_fwd(self, x, w, res=None, act: str | None = None):
+    def linear_fwd(self, x, w, res=None, act: str | None = None, gather=None):
         """y = x @ wᵀ (+res).  act == "gelu" → returns (pre, gelu(pre))."""
         y = x @ w.t()
         if act == "gelu":
@@ -220,10 +220,10 @@ class TorchBackend:
         return out.view(B * T, 3 * H * C)
 
     # ---------------------------------------------------------------- LM head + cross-entropy (K10,K11)
-    def lmhead_logits(self, h, w):
+    def lmhead_logits(self, h, w, gather=None):
         return h @ w.t()
 
-    def lmhead_ce(self, h, w, targets, dw_acc=None, grad_scale: float = 0.0, chunk: int = 8192):
+    def lmhead_ce(self, h, w, targets, dw_acc=None, grad_scale: float = 0.0, chunk: int = 8192, gather=None):
         """Σ_tokens CE(h·wᵀ, targets) in fp32 without materialising [M,V] at once.
 
         If ``dw_acc`` is given the backward is fused: returns (loss_sum, dh) and accumulates

@@ -97,7 +97,7 @@ class FSDPEngine:
         self._micro_is_last = True
         self._pending_reduce: tp.List[int] = []
         self.last_grad_norm: torch.Tensor | None = None
-        if self.comm == "fused":
+        if self.comm == "fused" and self.S > 1:
             from .fused import FusedComm
             self.fused = FusedComm(self)
 
@@ -163,6 +163,8 @@ class FSDPEngine:
     # ------------------------------------------------------------------ WeightProvider protocol
     def acquire(self, unit: int) -> tp.Dict[str, torch.Tensor]:
         u = self.units[unit]
+        if self.gather_mode == "layer" and self.fused is not None:
+            return self._acquire_fused_layer(unit)
         if self.gather_mode == "step":
             self.gather_all()
         else:
@@ -176,6 +178,28 @@ class FSDPEngine:
         if self.cuda and u.gathered_event is not None:
             torch.cuda.current_stream().wait_event(u.gathered_event)
         return P.unit_views(u.spec, u.lp_full)
+
+    def _acquire_fused_layer(self, unit: int) -> tp.Dict[str, torch.Tensor]:
+        """ZeRO-3 gathers with no collective call: the unit's first K-major GEMM pulls the remote chunks itself
+        (all-gather ⊕ GEMM); units whose first consumer is not such a GEMM use the stand-alone NVLink pull kernel."""
+        u = self.units[unit]
+        spec = None
+        if u.lp_full is None:
+            if not self._pool_free:
+                raise RuntimeError("FSDP pool exhausted: a unit was acquired twice without release")
+            slot = self._pool_free.pop(0)
+            u.pool_slot = slot
+            u.lp_full = self._pool[slot][: u.padded]
+            u.lp_full[self.sr * u.shard:(self.sr + 1) * u.shard].copy_(u.lp_shard)       # local chunk
+            gemm_first = unit >= 1 and (self._direction >= 0 or self.cfg.engine.remat == "block")
+            if gemm_first:
+                spec = self.fused.gather_spec(u)
+            else:
+                self.fused.all_gather(u)
+        views = P.unit_views(u.spec, u.lp_full)
+        if spec is not None:
+            views["__gather__"] = spec
+        return views
 
     def _prefetch_candidates(self, unit: int) -> tp.List[int]:
         depth = max(1, self.cfg.engine.prefetch_depth)

@@ -29,12 +29,23 @@ import torch.distributed as dist
 from ..optim import step_scalars, clip_factor_from_sumsq
 
 
+class GatherSpec:
+    """Everything the all-gather ⊕ GEMM kernel needs to pull one unit's remote chunks while it multiplies (csrc/gemm.cu)."""
+
+    def __init__(self, peer_ptrs, local, flags, chunk_elems, target, rank, n_ctas):
+        self.peer_ptrs, self.local, self.flags = peer_ptrs, local, flags
+        self.chunk_elems, self.target, self.rank, self.n_ctas = chunk_elems, target, rank, n_ctas
+        self.done = False
+
+
+AG_CTAS = 32     # CTAs of the GEMM grid that first act as NVLink pullers (8 x 16-byte loads in flight per thread)
+
+
 class FusedComm:
     def __init__(self, engine):
         import torch.distributed._symmetric_memory as symm_mem
         from ..ops.b200_backend import load_ext
-        if engine.gather_mode != "step":
-            raise RuntimeError('comm="fused" keeps bf16 weights resident: use gather_mode="step" (or "auto")')
+        self.layer_mode = engine.gather_mode == "layer"
         self.ext = load_ext()
         self.e = engine
         mesh = engine.mesh
@@ -43,7 +54,10 @@ class FusedComm:
         dev = engine.device
         total = sum(u.padded for u in engine.units)
         self.grad_arena = symm_mem.empty(total, dtype=torch.float32, device=dev)
-        self.lp_arena = symm_mem.empty(total, dtype=engine.compute_dtype, device=dev)
+        # step mode: every rank holds the full gathered weights (peers push into it).  layer mode: only the local
+        # shards are symmetric (peers pull from them inside the consuming GEMM) and gathered copies live in a local pool.
+        lp_elems = total // self.world if self.layer_mode else total
+        self.lp_arena = symm_mem.empty(lp_elems, dtype=engine.compute_dtype, device=dev)
         self.pad = symm_mem.empty(4096, dtype=torch.int32, device=dev)
         self.grad_arena.zero_()
         self.lp_arena.zero_()
@@ -57,18 +71,28 @@ class FusedComm:
         self.pad_ptrs = [int(p) for p in self.h_pad.buffer_ptrs]
         use_mc = bool(int(__import__("os").environ.get("MIDGPT_MULTIMEM", "1")))
         self.mc_grad = int(self.h_grad.multicast_ptr) if use_mc and self.h_grad.has_multicast_support(dev.type, dev.index) else 0
-        self.mc_lp = int(self.h_lp.multicast_ptr) if use_mc and self.mc_grad else 0
+        self.mc_lp = int(self.h_lp.multicast_ptr) if use_mc and self.mc_grad and not self.layer_mode else 0
         self.epoch = 0
         # re-point the engine's per-unit buffers into the arenas
-        off = 0
+        off = soff = 0
         self.offsets: tp.Dict[int, int] = {}
+        self.shard_offsets: tp.Dict[int, int] = {}
         for i, u in enumerate(engine.units):
             self.offsets[i] = off
+            self.shard_offsets[i] = soff
             u.grad_full = self.grad_arena[off:off + u.padded]
-            u.lp_full = self.lp_arena[off:off + u.padded]
-            u.lp_shard = u.lp_full[self.rank * u.shard:(self.rank + 1) * u.shard]
+            if self.layer_mode:
+                u.lp_shard = self.lp_arena[soff:soff + u.shard]
+            else:
+                u.lp_full = self.lp_arena[off:off + u.padded]
+                u.lp_shard = u.lp_full[self.rank * u.shard:(self.rank + 1) * u.shard]
             u.lp_shard.copy_(u.master)
             off += u.padded
+            soff += u.shard
+        if self.layer_mode:
+            n_slots = len(engine._pool)
+            self.slot_flags = [torch.zeros(8, dtype=torch.int32, device=dev) for _ in range(n_slots)]
+            self.slot_calls = [0] * n_slots
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._pushed = False
         self._barrier()          # every rank has zeroed / initialised its arenas
@@ -82,10 +106,29 @@ class FusedComm:
         self.ext.xrank_barrier(self.pad_ptrs, self.rank, 0, self.epoch)
 
     def all_gather(self, u) -> None:
-        """Only the very first gather (initial weights) moves data here; afterwards AdamW pushes keep lp_arena current."""
+        """step mode: only the very first gather (initial weights) moves data; afterwards AdamW pushes keep lp_arena current.
+        layer mode: stand-alone NVLink pull (used where no K-major GEMM is the first consumer, e.g. the embedding)."""
+        if self.layer_mode:
+            self.ext.ag_pull(self._peer_shard_ptrs(u), u.lp_full, u.shard, self.rank, self._next_flags(u), AG_CTAS)
+            return
         if self._pushed:
             return
         dist.all_gather_into_tensor(u.lp_full, u.lp_shard, group=self.e.mesh.shard_group)
+
+    # ---- layer mode helpers ------------------------------------------------
+    def _peer_shard_ptrs(self, u) -> tp.List[int]:
+        i = self.e.units.index(u)
+        return [p + self.shard_offsets[i] * 2 for p in self.lp_ptrs]
+
+    def _next_flags(self, u) -> torch.Tensor:
+        self.slot_calls[u.pool_slot] += 1
+        return self.slot_flags[u.pool_slot]
+
+    def gather_spec(self, u) -> GatherSpec:
+        """Descriptor consumed by the first K-major GEMM of the unit: that kernel performs the all-gather itself."""
+        flags = self._next_flags(u)
+        return GatherSpec(self._peer_shard_ptrs(u), u.lp_full, flags, u.shard, self.slot_calls[u.pool_slot] * AG_CTAS,
+                          self.rank, AG_CTAS)
 
     def reduce_scatter(self, u) -> None:
         """Called on the comm stream once this rank's backward of unit ``u`` is complete."""
@@ -106,6 +149,10 @@ class FusedComm:
         sc = step_scalars(e.count, e.cfg)
         clip1 = clip.reshape(1).float()
         for i, u in enumerate(e.units):
+            if self.layer_mode:      # shards stay local (peers pull them later from inside their GEMMs)
+                self.ext.adamw_step(u.master, u.exp_avg, u.exp_avg_sq, u.grad_shard, u.lp_shard, clip1, sc.lr, sc.b1, sc.b2, sc.eps,
+                                    sc.wd_over_lr_peak, sc.bc1, sc.bc2, False)
+                continue
             off = self.offsets[i] + self.rank * u.shard
             self.ext.adamw_allgather(u.master, u.exp_avg, u.exp_avg_sq, u.grad_shard, self.lp_ptrs, self.mc_lp, off, clip1,
                                      sc.lr, sc.b1, sc.b2, sc.eps, sc.wd_over_lr_peak, sc.bc1, sc.bc2)
