@@ -64,3 +64,31 @@ def test_loss_decreases_single_process():
     x, y = _batches(cfg, 1)[0]
     losses = [tr.train_step(x, y).item() for _ in range(12)]
     assert losses[-1] < losses[1] - 0.3, losses
+
+
+def _run_hsdp(rank, world, n_steps):
+    """world=4 as 2 shard groups of 2 (HSDP: reduce-scatter inside a group, all-reduce across replicas — X5)."""
+    from midgpt_b200.train import Trainer
+    from midgpt_b200.parallel import dist as D
+    torch.manual_seed(0)
+    cfg = _tiny_cfg(True, "step")
+    mesh = D.make_mesh(True, "cpu", max_shard=2)
+    assert mesh.shard_size == 2 and mesh.replica_size == 2
+    tr = Trainer(cfg, mesh=mesh)
+    losses = []
+    for x, y in _batches(cfg, n_steps):
+        G, B, T = cfg.g_accum_iters, cfg.batch_size, cfg.model_config.block_size
+        xs = x.view(G, B, T)[:, rank * B // world:(rank + 1) * B // world].reshape(-1, T)
+        ys = y.view(G, B, T)[:, rank * B // world:(rank + 1) * B // world].reshape(-1, T)
+        losses.append(tr.train_step(xs, ys).item())
+    return losses, {k: v.clone() for k, v in tr.engine.full_state("master").items()}
+
+
+def test_hsdp_world4_equals_single():
+    n_steps = 3
+    ref_losses, ref_state, _ = _run(0, 1, False, "step", n_steps)
+    outs = run_distributed(_run_hsdp, 4, n_steps)
+    for losses, state in outs:
+        assert torch.allclose(torch.tensor(losses), torch.tensor(ref_losses), rtol=1e-5, atol=1e-6)
+        for k in ref_state:
+            assert torch.allclose(torch.as_tensor(state[k]), ref_state[k], rtol=1e-4, atol=1e-6), k
