@@ -80,14 +80,15 @@ MG_DEVICE void st_swizzled_chunk(uint8_t* tile, int rows, int r, int cc, uint4 v
 template <int C>
 struct FwdCfg {
   static constexpr int BQ = 128;
-  static constexpr int BKV = (C == 64) ? 128 : 64;
+  static constexpr int BKV = 64;
   static constexpr int Q_BYTES = BQ * C * 2;
   static constexpr int K_BYTES = BKV * C * 2;
   static constexpr int V_BYTES = BKV * C * 2;
   static constexpr int P_BYTES = BQ * BKV * 2;
   static constexpr int SMEM = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES + 256;
   static constexpr int TMEM_COLS = 256;
-  static constexpr int S_COL = 0, O_COL = BKV;
+  static constexpr int S_COL = 0, O_COL = 2 * BKV;      // two S buffers (QK of tile j+1 overlaps the softmax of tile j), then O
+  static_assert(2 * BKV + C <= TMEM_COLS, "TMEM budget");
 };
 
 template <int C>
@@ -110,10 +111,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* k_empty = bars + 3;       // 2
   uint64_t* v_full = bars + 5;        // 2
   uint64_t* v_empty = bars + 7;       // 2
-  uint64_t* s_full = bars + 9;        // 1
-  uint64_t* p_full = bars + 10;       // 1 (128 arrivals)
-  uint64_t* pv_done = bars + 11;      // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_full = bars + 9;        // 2 (one per S buffer)
+  uint64_t* p_full = bars + 11;       // 1 (128 arrivals)
+  uint64_t* pv_done = bars + 12;      // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;          // heavy (late) query tiles first
@@ -125,7 +126,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_done, 1);
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(p_full, 128); mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -167,18 +168,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < C / 16; ++k) {
           const uint32_t blk = (k * 16) / 64, in = (k * 16) % 64;
-          umma_bf16_ss(tmem + Cfg::S_COL, make_smem_desc(q_base + blk * (BQ * 128) + in * 2, 16, 1024),
+          umma_bf16_ss(tmem + Cfg::S_COL + st * BKV, make_smem_desc(q_base + blk * (BQ * 128) + in * 2, 16, 1024),
                        make_smem_desc(k_base + blk * (BKV * 128) + in * 2, 16, 1024), idesc_s, k != 0);
         }
         umma_commit(&k_empty[st]);
-        umma_commit(s_full);
+        umma_commit(&s_full[st]);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
+      if (n_kv > 1) issue_qk(1);           // S is double buffered: the next QKᵀ never waits for the softmax
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(p_full, j & 1);          // P_j is in smem and S_j has been fully read
         tc_fence_after();
-        if (j + 1 < n_kv) issue_qk(j + 1);
         const int st = j & 1;
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after();
@@ -191,6 +192,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
+        if (j + 2 < n_kv) issue_qk(j + 2);   // reuses S buffer j&1, which the softmax warps released at p_full(j)
       }
     }
   } else {
@@ -201,9 +203,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sl2 = scale * kLog2e;
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const int kv0 = j * BKV;
+      const uint32_t s_col = Cfg::S_COL + (j & 1) * BKV;
       const bool need_mask = (kv0 + BKV - 1 > q0);          // tile touches or crosses the diagonal
       constexpr int NCH = BKV / 32;
       constexpr bool KEEP = (BKV == 64);                     // S row stays in registers between the two passes
@@ -214,7 +217,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int ch = 0; ch < NCH; ++ch) {
         uint32_t tmp[32];
         uint32_t(&r)[32] = KEEP ? sreg[KEEP ? ch : 0] : tmp;
-        tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+        tmem_ld_x32(t_lane + s_col + ch * 32, r);
         if (!KEEP) {
           tmem_ld_wait();
           if (need_mask) {
@@ -269,7 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t tmp[32];
         uint32_t(&r)[32] = KEEP ? sreg[KEEP ? ch : 0] : tmp;
         if (!KEEP) {
-          tmem_ld_x32(t_lane + Cfg::S_COL + ch * 32, r);
+          tmem_ld_x32(t_lane + s_col + ch * 32, r);
           tmem_ld_wait();
         }
         float p[32];

@@ -71,7 +71,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
   return v;
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, bool AG = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
@@ -113,7 +113,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   // ---- fused all-gather: producer CTAs pull the peers' chunks (ring order starting after the local chunk)
-  const bool gather = p.ag.n_ctas > 0;
+  const bool gather = AG && p.ag.n_ctas > 0;      // compile-time off for the plain kernels: zero cost on the common path
   if (gather && static_cast<int>(blockIdx.x) < p.ag.n_ctas) {
     const long long n16 = p.ag.chunk_elems >> 3;
     for (int k = 1; k < p.ag.world; ++k) {
@@ -403,10 +403,10 @@ CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, long long rows, long l
   return m;
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, bool AG = false>
 static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tD2,
                        const GemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI>;
+  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, AG>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -458,6 +458,12 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
   if (ag) {
     p.ag = *ag;
     if (a_mn || b_mn) throw std::runtime_error("all-gather ⊕ GEMM needs K-major operands");
+  }
+  if (ag) {
+    if (epi == EPI_STORE) return launch_one<false, false, EPI_STORE, true>(tA, tB, tD, tD2, p, num_sms, stream);
+    if (epi == EPI_GELU) return launch_one<false, false, EPI_GELU, true>(tA, tB, tD, tD2, p, num_sms, stream);
+    if (epi == EPI_RESIDUAL) return launch_one<false, false, EPI_RESIDUAL, true>(tA, tB, tD, tD2, p, num_sms, stream);
+    throw std::runtime_error("all-gather ⊕ GEMM: unsupported epilogue");
   }
 #define MG_CASE(AM, BM_, E) \
   if (a_mn == AM && b_mn == BM_ && epi == E) return launch_one<AM, BM_, E>(tA, tB, tD, tD2, p, num_sms, stream);
