@@ -30,7 +30,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;             // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;             // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int CSTAGE_BYTES = BM * 128;                 // 128 rows x 128 B (64 bf16 or 32 fp32 per row)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 256 + 1024;  // + barriers + align slack
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 512 + 1024;  // + barriers + align slack
 constexpr int GROUP_M = 8;
 constexpr int NUM_THREADS = 320;     // 2 control warps + 8 epilogue warps
 constexpr int EPI_THREADS = 256;
@@ -112,38 +112,64 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- fused all-gather: producer CTAs pull the peers' chunks (ring order starting after the local chunk)
+  // ---- fused all-gather: the first n_ctas CTAs are in-kernel NVLink copy engines.  One thread per CTA drives a ring of
+  // 16 KB bulk copies peer HBM -> smem -> local HBM (cp.async.bulk, ~190 KB in flight per CTA, no registers involved),
+  // publishing one flag per peer chunk; the remaining CTAs run the GEMM and poll the flags of the chunks they need.
   const bool gather = AG && p.ag.n_ctas > 0;      // compile-time off for the plain kernels: zero cost on the common path
   if (gather && static_cast<int>(blockIdx.x) < p.ag.n_ctas) {
-    const long long n16 = p.ag.chunk_elems >> 3;
-    for (int k = 1; k < p.ag.world; ++k) {
-      const int c = (p.ag.rank + k) % p.ag.world;
-      const uint4* src = reinterpret_cast<const uint4*>(p.ag.peer[c]);
-      uint4* dst = reinterpret_cast<uint4*>(p.ag.local + static_cast<long long>(c) * p.ag.chunk_elems);
-      // 8 independent 16-byte NVLink loads in flight per thread (peer latency is ~2 us; bandwidth needs depth)
-      const long long stride = static_cast<long long>(p.ag.n_ctas) * blockDim.x;
-      for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n16; i0 += stride * 8) {
-        uint4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const long long i = i0 + u * stride;
-          if (i < n16)
-            asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + i));
+    if (threadIdx.x == 0) {
+      constexpr uint32_t SUB = 16384;
+      constexpr int NB = (STAGES * STAGE_BYTES) / SUB;                       // the GEMM's smem ring is free in a puller CTA
+      uint64_t* pbar = reinterpret_cast<uint64_t*>(tmem_slot + 2);           // NB mbarriers after the GEMM's own
+      for (int i = 0; i < NB; ++i) mbar_init(&pbar[i], 1);
+      fence_barrier_init();
+      const long long chunk_bytes = p.ag.chunk_elems * 2;
+      const long long per_cta = ((chunk_bytes / p.ag.n_ctas) + SUB - 1) / SUB * SUB;
+      const long long lo = static_cast<long long>(blockIdx.x) * per_cta;
+      const long long hi = min(chunk_bytes, lo + per_cta);
+      uint32_t use[NB];
+      for (int i = 0; i < NB; ++i) use[i] = 0;
+      for (int k = 1; k < p.ag.world; ++k) {
+        const int c = (p.ag.rank + k) % p.ag.world;
+        const char* src = reinterpret_cast<const char*>(p.ag.peer[c]);
+        char* dst = reinterpret_cast<char*>(p.ag.local) + static_cast<long long>(c) * chunk_bytes;
+        const long long n_sub = hi > lo ? (hi - lo + SUB - 1) / SUB : 0;
+        auto bytes_of = [&](long long i) {
+          const long long rem = hi - (lo + i * SUB);
+          return static_cast<uint32_t>(rem < static_cast<long long>(SUB) ? rem : static_cast<long long>(SUB));
+        };
+        long long issued = 0;
+        for (; issued < n_sub && issued < NB; ++issued) {
+          const int slot = static_cast<int>(issued % NB);
+          mbar_expect_tx(&pbar[slot], bytes_of(issued));
+          bulk_load_1d(smem + slot * SUB, src + lo + issued * SUB, bytes_of(issued), &pbar[slot]);
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const long long i = i0 + u * stride;
-          if (i < n16) dst[i] = v[u];
+        for (long long i = 0; i < n_sub; ++i) {
+          const int slot = static_cast<int>(i % NB);
+          mbar_wait(&pbar[slot], use[slot] & 1);
+          use[slot]++;
+          bulk_store_1d(dst + lo + i * SUB, smem + slot * SUB, bytes_of(i));
+          tma_commit_group();
+          if (i >= 1 && issued < n_sub) {
+            tma_wait_group_read<1>();                       // the store that used slot (i-1) has finished reading smem
+            const int rs = static_cast<int>(issued % NB);   // == (i-1) % NB
+            mbar_expect_tx(&pbar[rs], bytes_of(issued));
+            bulk_load_1d(smem + rs * SUB, src + lo + issued * SUB, bytes_of(issued), &pbar[rs]);
+            ++issued;
+          }
         }
-      }
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        asm volatile("fence.proxy.async.global;" ::: "memory");   // the data is consumed by TMA (async proxy)
+        tma_wait_group<0>();                                // all stores of this chunk slice are complete
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence();
         atomicAdd(p.ag.flags + c, 1u);
       }
     }
+    // copy-engine CTAs own no GEMM tiles: fall through to the common teardown
   }
+  const int n_pull = gather ? p.ag.n_ctas : 0;
+  const int tile0 = static_cast<int>(blockIdx.x) - n_pull;              // negative for copy-engine CTAs -> no tiles
+  const int tile_stride = static_cast<int>(gridDim.x) - n_pull;
+  const int my_first_tile = tile0 >= 0 ? tile0 : num_tiles;
 
   // tile -> (m_blk, n_blk).  With a fused gather the n-blocks are rotated so that locally-owned weight rows come first.
   const int n_rot = gather ? static_cast<int>(((static_cast<long long>(p.ag.rank) * p.ag.chunk_elems - p.ag.b_offset) / p.K) / BN) : 0;
@@ -166,7 +192,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = my_first_tile; tile < num_tiles; tile += tile_stride) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         if (gather) {
@@ -211,7 +237,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = my_first_tile; tile < num_tiles; tile += tile_stride, ++it) {
         const int buf = it & 1;
         const uint32_t tphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[buf], tphase ^ 1);
@@ -244,7 +270,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool issuer = (threadIdx.x == 64);      // first epilogue thread issues the TMA stores
     const uint32_t sw = (row & 7);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = my_first_tile; tile < num_tiles; tile += tile_stride, ++it) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int buf = it & 1;
@@ -415,7 +441,10 @@ static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  if (p.ag.n_ctas > grid) grid = p.ag.n_ctas < num_sms ? p.ag.n_ctas : num_sms;
+  if (AG && p.ag.n_ctas > 0) {                      // copy-engine CTAs come on top of the GEMM workers (all co-resident: 1 CTA / SM)
+    const int workers = num_tiles < num_sms - p.ag.n_ctas ? num_tiles : num_sms - p.ag.n_ctas;
+    grid = workers + p.ag.n_ctas;
+  }
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tA, tB, tD, tD2, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("gemm launch: ") + cudaGetErrorString(e));

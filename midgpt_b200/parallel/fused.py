@@ -38,7 +38,7 @@ class GatherSpec:
         self.done = False
 
 
-AG_CTAS = 32     # CTAs of the GEMM grid that first act as NVLink pullers (8 x 16-byte loads in flight per thread)
+AG_CTAS = 12     # CTAs of the all-gather ⊕ GEMM grid that act as NVLink copy engines (12 x 16 KB bulk copies in flight each)
 
 
 class FusedComm:
@@ -70,8 +70,8 @@ class FusedComm:
         self.lp_ptrs = [int(p) for p in self.h_lp.buffer_ptrs]
         self.pad_ptrs = [int(p) for p in self.h_pad.buffer_ptrs]
         use_mc = bool(int(__import__("os").environ.get("MIDGPT_MULTIMEM", "1")))
-        self.mc_grad = int(self.h_grad.multicast_ptr) if use_mc and self.h_grad.has_multicast_support(dev.type, dev.index) else 0
-        self.mc_lp = int(self.h_lp.multicast_ptr) if use_mc and self.mc_grad and not self.layer_mode else 0
+        self.mc_grad = int(self.h_grad.multicast_ptr or 0) if use_mc else 0          # 0 when NVLS multicast is unavailable
+        self.mc_lp = int(self.h_lp.multicast_ptr or 0) if use_mc and self.mc_grad and not self.layer_mode else 0
         self.epoch = 0
         # re-point the engine's per-unit buffers into the arenas
         off = soff = 0
