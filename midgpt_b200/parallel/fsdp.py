@@ -72,8 +72,12 @@ class FSDPEngine:
         mode = cfg.engine.gather_mode
         self.gather_mode = ("step" if mode == "auto" else mode) if self.S > 1 else "step"
         self.comm = cfg.engine.comm
+        self._comm_auto = self.comm == "auto"
         if self.comm == "auto":
-            self.comm = mesh.backend if mesh.backend != "none" else "none"
+            # product path when it applies (NVLink domain + hand-written backend), library collectives otherwise
+            fused_ok = (mesh.backend == "nccl" and self.S > 1 and getattr(backend, "name", "") == "b200"
+                        and self.gather_mode == "step")
+            self.comm = "fused" if fused_ok else (mesh.backend if mesh.backend != "none" else "none")
         self.comm_stream = torch.cuda.Stream(self.device) if self.cuda else None
         self.fused = None                                # parallel.fused.FusedComm when comm == "fused"
 
@@ -99,7 +103,14 @@ class FSDPEngine:
         self.last_grad_norm: torch.Tensor | None = None
         if self.comm == "fused" and self.S > 1:
             from .fused import FusedComm
-            self.fused = FusedComm(self)
+            try:
+                self.fused = FusedComm(self)
+            except Exception as e:
+                if not self._comm_auto:
+                    raise
+                print(f"[fsdp] WARNING: in-kernel NVLink path unavailable ({type(e).__name__}: {e}); falling back to NCCL collectives")
+                self.comm = mesh.backend
+                self._alloc_lp()
 
     # ------------------------------------------------------------------ low-precision weight buffers
     def _alloc_lp(self) -> None:
