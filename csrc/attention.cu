@@ -425,7 +425,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&do_full[s], 1); mbar_init(&qdo_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&do_full[s], 1); mbar_init(&qdo_empty[s], 2); }   // MMA commit + dQ drain
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 256); mbar_init(dv_done, 1); mbar_init(ds_ready, 256);
     mbar_init(dq_full, 1); mbar_init(dq_drained, 256);
     fence_barrier_init();
@@ -610,23 +610,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_drained);                     // TMEM side is done; the MMA warp may issue dP(it+1)
+      // staging: 32 fp32 columns per (column-half, round) = one [128 x 128 B] box; round 0 lives in the P/dS buffer, round 1
+      // (C = 128 only) in this tile's Q stage, which the TMA producer may not refill before the drain has released it.
+      uint8_t* stage_q = sQ + (it & 1) * Cfg::TILE;
 #pragma unroll
       for (int rd = 0; rd < ROUNDS; ++rd) {
-        uint8_t* stg = sPS + half * (128 * 128) + row * 128;     // [128 rows x 128 B] box per column-half
+        uint8_t* stg = (rd == 0 ? sPS : stage_q) + half * (128 * 128) + row * 128;
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<uint4*>(stg + ((g ^ (row & 7)) << 4)) = make_uint4(dq[rd][4 * g], dq[rd][4 * g + 1], dq[rd][4 * g + 2], dq[rd][4 * g + 3]);
-        fence_proxy_async_smem();
-        named_bar_sync(1, 256);
-        if (issuer) {
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (issuer) {
+#pragma unroll
+        for (int rd = 0; rd < ROUNDS; ++rd)
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh)
-            tma_reduce_add_3d(&tmdQ, sPS + hh * (128 * 128), h * C + hh * (C / 2) + rd * 32, q0, b);
-          tma_commit_group();
-          tma_wait_group_read<0>();
-        }
-        named_bar_sync(2, 256);                    // staging area reusable (next round / next tile's P)
+            tma_reduce_add_3d(&tmdQ, (rd == 0 ? sPS : stage_q) + hh * (128 * 128), h * C + hh * (C / 2) + rd * 32, q0, b);
+        tma_commit_group();
+        tma_wait_group_read<0>();
+        mbar_arrive(&qdo_empty[it & 1]);           // second arrival (first: the MMA commit) -> Q/dO stage may be refilled
       }
+      named_bar_sync(2, 256);                      // staging areas reusable (next tile's P)
     }
     // ---- epilogue: dV, dK (thread = kv row x column half).  The last dq_full wait also covers the final dV/dK MMAs.
     const int kv_idx = kv0 + row;
