@@ -12,6 +12,10 @@ void gemm_launch_ag_raw(const void* a, long long lda, const void* b, long long l
                         const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms, cudaStream_t stream,
                         const long long* peer_ptrs, void* local, unsigned int* flags, long long chunk_elems, long long b_offset,
                         unsigned int target, int world, int rank, int n_ctas);
+void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb, const float* sa, const float* sb, void* d, long long ldd,
+                     void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms,
+                     cudaStream_t stream);
+void quant_rows_e4m3(const void* x, void* q, float* dequant, int R, int C, cudaStream_t s);
 void rmsnorm_fwd(const void* x, void* y, float* rstd, int M, int D, float eps, cudaStream_t s);
 void rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* dres, void* dx, int M, int D, cudaStream_t s);
 void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const float* sin_t, const float* cos_t, void* qk,
@@ -109,6 +113,33 @@ void gemm_ag(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, int64_t ep
                          static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), num_sms_of(a), stream(),
                          pp.data(), local.data_ptr(), reinterpret_cast<unsigned int*>(flags.data_ptr()), chunk_elems, b_offset,
                          static_cast<unsigned int>(target), static_cast<int>(pp.size()), static_cast<int>(rank), static_cast<int>(n_ctas));
+}
+
+// row-wise e4m3 quantisation: returns (q uint8 [R,C], dequant fp32 [R])
+std::vector<at::Tensor> quant_rows_e4m3(const at::Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  CHECK_BF16(x); TORCH_CHECK(x.dim() == 2 && x.is_contiguous());
+  auto q = at::empty(x.sizes(), x.options().dtype(at::kByte));
+  auto dq = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  mg::quant_rows_e4m3(x.data_ptr(), q.data_ptr(), dq.data_ptr<float>(), x.size(0), x.size(1), stream());
+  return {q, dq};
+}
+// d = (a_q · b_qᵀ) ∘ (sa ⊗ sb) (+ epilogue), a_q [M,K] / b_q [N,K] e4m3 bytes
+void gemm_fp8(const at::Tensor& a, const at::Tensor& sa, const at::Tensor& b, const at::Tensor& sb, at::Tensor& d, int64_t epi,
+              const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& aux) {
+  c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(a.scalar_type() == at::kByte && b.scalar_type() == at::kByte && a.is_contiguous() && b.is_contiguous());
+  CHECK_F32(sa); CHECK_F32(sb); CHECK_BF16(d); CHECK_2D_ROWMAJOR(d);
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K && d.size(0) == M && d.size(1) == N && sa.numel() == M && sb.numel() == N);
+  TORCH_CHECK(K % 16 == 0 && N % 64 == 0, "gemm_fp8: K must be a multiple of 16 and N of 64");
+  const void* auxp = nullptr; long long ld_aux = 0;
+  if (epi == 1) { TORCH_CHECK(aux.has_value()); CHECK_BF16(*aux); auxp = aux->data_ptr(); ld_aux = aux->stride(0); }
+  void* d2p = nullptr; long long ldd2 = 0;
+  if (epi == 2) { TORCH_CHECK(d2.has_value()); CHECK_BF16(*d2); d2p = d2->data_ptr(); ldd2 = d2->stride(0); }
+  mg::gemm_fp8_launch(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), sa.data_ptr<float>(), sb.data_ptr<float>(), d.data_ptr(),
+                      d.stride(0), d2p, ldd2, auxp, ld_aux, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K),
+                      static_cast<int>(epi), num_sms_of(a), stream());
 }
 
 std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, double eps) {
@@ -271,6 +302,8 @@ void ag_pull(std::vector<int64_t> lp_ptrs, at::Tensor& local, int64_t shard_elem
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM with fused epilogues");
   m.def("gemm_ag", &gemm_ag, "all-gather (NVLink pull) fused with the tcgen05 GEMM");
+  m.def("quant_rows_e4m3", &quant_rows_e4m3);
+  m.def("gemm_fp8", &gemm_fp8, "tcgen05 kind::f8f6f4 GEMM on row-scaled e4m3 operands");
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("qkln_rope_fwd", &qkln_rope_fwd);

@@ -195,6 +195,15 @@ MG_DEVICE void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, u
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 8-bit float inputs (e4m3 / e5m2), fp32 accumulation: kind::f8f6f4, K = 32 per instruction
+MG_DEVICE void umma_fp8_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // A operand from TMEM (used by attention: P·V with P kept in tensor memory)
 MG_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -270,6 +279,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
          | (b_mn_major << 16)      // B major
          | ((N >> 3) << 17)        // N / 8
          | ((M >> 4) << 24);       // M / 16
+}
+
+// Instruction descriptor for kind::f8f6f4 with e4m3 x e4m3 -> fp32 (format code 0 = E4M3), both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(uint32_t M, uint32_t N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace mg

@@ -456,6 +456,68 @@ void dropout(const void* x, void* y, long long n, float p, unsigned long long se
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row-wise e4m3 quantisation for the FP8 forward GEMMs: q[r,:] = round_e4m3(x[r,:] * 448/amax_r), dequant[r] = amax_r/448.
+// One warp per row, the row stays in registers between the amax reduction and the conversion (single pass over HBM).
+// ------------------------------------------------------------------------------------------------
+MG_DEVICE uint32_t pack4_e4m3(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+template <int MAXV>
+__global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q,
+                                                              float* __restrict__ dequant, int R, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const int nvec = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(warp) * C);
+  uint4 v[MAXV];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      v[i] = __ldg(xr + j);
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(f[e]));
+    }
+  }
+  amax = fmaxf(warp_max(amax), 1e-12f);
+  const float scale = 448.f / amax;
+  if (lane == 0) dequant[warp] = amax / 448.f;
+  uint2* qr = reinterpret_cast<uint2*>(q + static_cast<size_t>(warp) * C);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      float f[8];
+      unpack8(v[i], f);
+      qr[j] = make_uint2(pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale),
+                         pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale));
+    }
+  }
+}
+void quant_rows_e4m3(const void* x, void* q, float* dequant, int R, int C, cudaStream_t s) {
+  if (C % 8) throw std::runtime_error("quant_rows_e4m3: C must be a multiple of 8");
+  const int nvec = C / 8;
+  auto launch = [&](auto mv) {
+    constexpr int MAXV = decltype(mv)::value;
+    quant_rows_e4m3_kernel<MAXV><<<(R + 7) / 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), dequant, R, C);
+  };
+  if (nvec <= 32) launch(std::integral_constant<int, 1>());
+  else if (nvec <= 64) launch(std::integral_constant<int, 2>());
+  else if (nvec <= 128) launch(std::integral_constant<int, 4>());
+  else if (nvec <= 256) launch(std::integral_constant<int, 8>());
+  else if (nvec <= 512) launch(std::integral_constant<int, 16>());
+  else if (nvec <= 1024) launch(std::integral_constant<int, 32>());
+  else throw std::runtime_error("quant_rows_e4m3: row longer than 8192 elements");
+  check_launch("quant_rows_e4m3");
+}
+
+// ------------------------------------------------------------------------------------------------
 // Optimizer: Σ g² and the fused clip · Adam · independent-WD · LR · bf16 cast sweep over one fp32 shard
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ out) {

@@ -63,6 +63,8 @@ struct GemmParams {
   int M, N, K;
   int accumulate;
   GatherParams ag;
+  const float* row_scale_a;         // FP8 only: de-quantisation multipliers, one per row of A (token) …
+  const float* row_scale_b;         // … and one per row of B (output feature); acc[m,n] *= sa[m] * sb[n]
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -71,7 +73,9 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
   return v;
 }
 
-template <bool A_MN, bool B_MN, int EPI, bool AG = false>
+// FP8 = true: A and B hold e4m3 bytes (row-wise scaled, see quant_rows_e4m3 in elementwise.cu); the smem/TMA byte geometry
+// is unchanged (128-byte rows = 128 fp8 elements = one BK), tcgen05.mma runs kind::f8f6f4 with K = 32 per instruction.
+template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
@@ -89,7 +93,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_k = (p.K + BK - 1) / BK;
+  constexpr int BKE = FP8 ? 2 * BK : BK;            // elements per k-block (a k-block is always 128 bytes per row)
+  const int num_k = (p.K + BKE - 1) / BKE;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -213,14 +218,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* sA = smem + stage * STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
           if (!A_MN) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BKE, m_blk * BM);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
               tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
           }
           if (!B_MN) {
-            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BKE, n_blk * BN);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
@@ -233,7 +238,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BM, BN) : make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -254,7 +259,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                      : make_smem_desc(a_base + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, BK * 128, 1024)
                                      : make_smem_desc(b_base + k * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (FP8) umma_fp8_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -323,6 +329,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_wait();
           const int col0 = n_blk * BN + c * 64;
           const bool valid = (grow < p.M) && (col0 < p.N);
+          if (FP8) {
+            const float sa = grow < p.M ? __ldg(p.row_scale_a + grow) : 0.f;
+            const float4* sb4 = reinterpret_cast<const float4*>(p.row_scale_b + col0 + half * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 sb = (col0 + half * 32 + 4 * j < p.N) ? __ldg(sb4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * sa * sb.x);
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * sa * sb.y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * sa * sb.z);
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * sa * sb.w);
+            }
+          }
           uint8_t* rowp = sbuf + row * 128;
           if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
             const uint4* ap = reinterpret_cast<const uint4*>(p.aux + grow * p.ld_aux + col0) + half * 4;
@@ -417,7 +435,8 @@ CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, long long rows, long l
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                           : (elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   CUresult r = get_encode()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -429,10 +448,10 @@ CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, long long rows, long l
   return m;
 }
 
-template <bool A_MN, bool B_MN, int EPI, bool AG = false>
+template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false>
 static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tD2,
                        const GemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, AG>;
+  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, AG, FP8>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -483,7 +502,7 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
   CUtensorMap tB = b_mn ? make_tmap_2d(b, 2, K, N, ldb, 64, BK) : make_tmap_2d(b, 2, N, K, ldb, BK, BN);
   CUtensorMap tD = (epi == EPI_F32) ? make_tmap_2d(d, 4, M, N, ldd, 32, BM) : make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
-  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}};
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, nullptr, nullptr};
   if (ag) {
     p.ag = *ag;
     if (a_mn || b_mn) throw std::runtime_error("all-gather ⊕ GEMM needs K-major operands");
@@ -508,6 +527,21 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
   MG_CASE(true, false, EPI_F32)
 #undef MG_CASE
   throw std::runtime_error("gemm_launch: unsupported (a_mn, b_mn, epilogue) combination");
+}
+
+// FP8 forward GEMM: a [M,K] and b [N,K] hold e4m3 bytes with per-row de-quantisation scales sa [M], sb [N]; d (bf16) = (a·bᵀ)∘(sa⊗sb).
+void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb, const float* sa, const float* sb, void* d, long long ldd,
+                     void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms,
+                     cudaStream_t stream) {
+  CUtensorMap tA = make_tmap_2d(a, 1, M, K, lda, 2 * BK, BM);
+  CUtensorMap tB = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN);
+  CUtensorMap tD = make_tmap_2d(d, 2, M, N, ldd, 64, BM);
+  CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, sa, sb};
+  if (epi == EPI_STORE) return launch_one<false, false, EPI_STORE, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
+  if (epi == EPI_GELU) return launch_one<false, false, EPI_GELU, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
+  if (epi == EPI_RESIDUAL) return launch_one<false, false, EPI_RESIDUAL, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
+  throw std::runtime_error("gemm_fp8: unsupported epilogue");
 }
 
 }  // namespace mg

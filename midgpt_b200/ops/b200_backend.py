@@ -47,7 +47,10 @@ class QKV(tp.NamedTuple):
 class B200Backend:
     name = "b200"
 
-    def __init__(self, device: torch.device):
+    def __init__(self, device: torch.device, fp8: bool = False):
+        self.fp8 = fp8
+        self._wq: tp.Dict[int, tp.Tuple[int, torch.Tensor, torch.Tensor]] = {}
+        self._wver = 0
         if device.type != "cuda":
             raise RuntimeError("B200Backend needs a CUDA device")
         cap = torch.cuda.get_device_capability(device)
@@ -106,12 +109,40 @@ class B200Backend:
         self.launches += 1
         return self.ext.rmsnorm_bwd(dy, x, rstd, dres)
 
+    # ---------------------------------------------------------------- FP8 helpers
+    def notify_weights_updated(self) -> None:
+        """Called by the engine after every optimizer step: cached e4m3 weights are stale."""
+        self._wver += 1
+
+    def _quant_weight(self, w):
+        key = (w.data_ptr(), tuple(w.shape))
+        hit = self._wq.get(key)
+        if hit is None or hit[0] != self._wver:
+            q, s = self.ext.quant_rows_e4m3(w.contiguous())
+            self.launches += 1
+            hit = (self._wver, q, s)
+            self._wq[key] = hit
+        return hit[1], hit[2]
+
+    def _linear_fwd_fp8(self, x, w, y, epi, d2=None, aux=None):
+        xq, sx = self.ext.quant_rows_e4m3(x)
+        wq, sw = self._quant_weight(w)
+        self.ext.gemm_fp8(xq, sx, wq, sw, y, epi, d2, aux)
+        self.launches += 2
+
     # ---------------------------------------------------------------- linear
     def linear_fwd(self, x, w, res=None, act=None, gather=None):
         M, N = x.shape[0], w.shape[0]
         y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
         if gather is not None and gather.done:
             gather = None
+        if self.fp8 and gather is None and x.is_contiguous() and w.shape[1] % 16 == 0 and N % 64 == 0:
+            if act == "gelu":
+                a = torch.empty_like(y)
+                self._linear_fwd_fp8(x, w, y, EPI_GELU, d2=a)
+                return y, a
+            self._linear_fwd_fp8(x, w, y, EPI_RESIDUAL if res is not None else EPI_STORE, aux=res)
+            return y
         if act == "gelu":
             a = torch.empty_like(y)
             self._gemm(x, False, w, False, y, EPI_GELU, d2=a, gather=gather)

@@ -320,6 +320,8 @@ class FSDPEngine:
         self.count += 1
         self._need_gather = True
         self.last_grad_norm = gnorm
+        if hasattr(be, "notify_weights_updated"):
+            be.notify_weights_updated()
         return gnorm
 
     def current_lr(self) -> float:

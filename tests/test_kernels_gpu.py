@@ -171,3 +171,25 @@ def test_flash_attention_fwd_bwd(be, ref, B, T, H, C):
     dqkv_r = ref.attention_bwd(do.float(), packed, o_r, lse_r, B, T, H, C)
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         assert rel_err(dqkv[:, sl], dqkv_r[:, sl]) < 1.5e-2, name
+
+
+# ----------------------------------------------------------------------------------------------- FP8
+def test_fp8_quant_and_gemm(be):
+    torch.manual_seed(9)
+    M, N, K = 512, 768, 1024
+    x, w, res = rnd(M, K), rnd(N, K, scale=K ** -0.5), rnd(M, N)
+    q, s = be.ext.quant_rows_e4m3(x)
+    deq = q.view(torch.float8_e4m3fn).float() * s[:, None]
+    assert rel_err(deq, x) < 4e-2                       # e4m3 has 3 mantissa bits
+    assert torch.allclose(s, x.float().abs().amax(1) / 448, rtol=1e-3)
+    from midgpt_b200.ops.b200_backend import B200Backend
+    be8 = B200Backend(torch.device("cuda", 0), fp8=True)
+    wq, sw = be8.ext.quant_rows_e4m3(w)
+    ref = (q.view(torch.float8_e4m3fn).float() * s[:, None]) @ (wq.view(torch.float8_e4m3fn).float() * sw[:, None]).t()
+    y = be8.linear_fwd(x, w)
+    assert rel_err(y, ref) < 6e-3                       # exact up to bf16 output rounding given the quantised operands
+    assert rel_err(y, x.float() @ w.float().t()) < 6e-2
+    y2 = be8.linear_fwd(x, w, res=res)
+    assert rel_err(y2, ref + res.float()) < 6e-3
+    pre, act = be8.linear_fwd(x, w, act="gelu")
+    assert rel_err(pre, ref) < 6e-3 and rel_err(act, torch.nn.functional.gelu(pre.float(), approximate="tanh")) < 6e-3

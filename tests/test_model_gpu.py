@@ -36,6 +36,23 @@ def test_b200_backend_matches_torch_backend_over_steps():
         assert err < 2e-2, (k, err)
 
 
+def test_fp8_forward_training_tracks_bf16():
+    """e4m3 forward GEMMs (row-scaled) with bf16 backward: same loss trajectory within fp8 noise."""
+    from midgpt_b200.train import Trainer
+    ca, cb = _cfg("b200"), _cfg("b200")
+    ca.engine.fp8 = True
+    a, b = Trainer(ca), Trainer(cb)
+    g = torch.Generator().manual_seed(2)
+    la, lb = [], []
+    for _ in range(8):
+        x = torch.randint(0, 65, (8, 256), generator=g, dtype=torch.int32).cuda()
+        y = torch.randint(0, 65, (8, 256), generator=g, dtype=torch.int32).cuda()
+        la.append(a.train_step(x, y).item())
+        lb.append(b.train_step(x, y).item())
+    assert all(abs(p - q) < 6e-2 for p, q in zip(la, lb)), (la, lb)
+    assert la[-1] < la[0]
+
+
 def test_smoke_entry_runs():
     import __graft_entry__ as ge
     ge.smoke()
