@@ -92,12 +92,12 @@ def main():
     x = torch.randn(M, K, device=dev).bfloat16()
     local = torch.zeros(unit, dtype=torch.bfloat16, device=dev)
     local[rank * shard:(rank + 1) * shard].copy_(lps)
-    flags = torch.zeros(8, dtype=torch.int32, device=dev)
+    flags = torch.zeros(4096, dtype=torch.int32, device=dev)
     calls = [0]
 
     def ag_gemm():
         calls[0] += 1
-        spec = GatherSpec(sp, local, flags, shard, calls[0] * AG_CTAS, rank, AG_CTAS)
+        spec = GatherSpec(sp, local, flags, shard, calls[0], rank, AG_CTAS)
         be.linear_fwd(x, local[: N * K].view(N, K), gather=spec)
 
     t = timeit(ag_gemm, pre=barrier)

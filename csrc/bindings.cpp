@@ -104,6 +104,7 @@ void gemm_ag(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, int64_t ep
   const int64_t b_offset = (reinterpret_cast<const char*>(b.data_ptr()) - reinterpret_cast<const char*>(local.data_ptr())) / 2;
   TORCH_CHECK(b_offset >= 0 && b_offset + N * K <= local.numel(), "gemm_ag: b must live inside the local unit buffer");
   TORCH_CHECK(chunk_elems % 8 == 0 && static_cast<int64_t>(peer_ptrs.size()) * chunk_elems <= local.numel());
+  TORCH_CHECK(flags.numel() >= (static_cast<int64_t>(peer_ptrs.size()) * chunk_elems + 32767) / 32768, "gemm_ag: flags needs one word per 32768-element segment");
   const void* auxp = nullptr; long long ld_aux = 0;
   if (epi == 1 || epi == 3) { TORCH_CHECK(aux.has_value()); CHECK_BF16(*aux); auxp = aux->data_ptr(); ld_aux = aux->stride(0); }
   void* d2p = nullptr; long long ldd2 = 0;

@@ -50,12 +50,13 @@ enum Epilogue : int {
 struct GatherParams {
   void* peer[8];                    // peer[c] = rank c's bf16 shard (symmetric memory), length chunk_elems
   __nv_bfloat16* local;             // local gathered unit buffer, world * chunk_elems elements
-  unsigned int* flags;              // one counter per chunk; chunk c is complete when flags[c] == target
+  unsigned int* flags;              // one word per SEG_ELEMS-element segment of the unit; == target (epoch) once the segment landed
   long long chunk_elems;            // elements per chunk (multiple of 8)
   long long b_offset;               // element offset of the B matrix inside the unit buffer
-  unsigned int target;
+  unsigned int target;              // epoch of this call (monotonically increasing per flags buffer)
   int world, rank, n_ctas;
 };
+constexpr long long SEG_ELEMS = 32768;   // 64 KB of bf16: flag granularity of the fused gather (a 256-row weight tile at K=2048 is 16 segments)
 
 struct GemmParams {
   const __nv_bfloat16* aux;
@@ -123,50 +124,89 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool gather = AG && p.ag.n_ctas > 0;      // compile-time off for the plain kernels: zero cost on the common path
   if (gather && static_cast<int>(blockIdx.x) < p.ag.n_ctas) {
     if (threadIdx.x == 0) {
-      constexpr uint32_t SUB = 16384;
-      constexpr int NB = (STAGES * STAGE_BYTES) / SUB;                       // the GEMM's smem ring is free in a puller CTA
+      constexpr uint32_t SUB = 16384;                                         // bytes per bulk copy
+      constexpr int NB = (STAGES * STAGE_BYTES) / SUB;                       // the GEMM's smem ring is free in a copy-engine CTA
+      constexpr int SUBS_PER_SEG = static_cast<int>(SEG_ELEMS * 2 / SUB);    // 8
       uint64_t* pbar = reinterpret_cast<uint64_t*>(tmem_slot + 2);           // NB mbarriers after the GEMM's own
       for (int i = 0; i < NB; ++i) mbar_init(&pbar[i], 1);
       fence_barrier_init();
-      const long long chunk_bytes = p.ag.chunk_elems * 2;
-      const long long per_cta = ((chunk_bytes / p.ag.n_ctas) + SUB - 1) / SUB * SUB;
-      const long long lo = static_cast<long long>(blockIdx.x) * per_cta;
-      const long long hi = min(chunk_bytes, lo + per_cta);
+      const long long unit_elems = p.ag.chunk_elems * p.ag.world;
+      const long long n_seg = (unit_elems + SEG_ELEMS - 1) / SEG_ELEMS;
+      const long long loc0 = static_cast<long long>(p.ag.rank) * p.ag.chunk_elems, loc1 = loc0 + p.ag.chunk_elems;
       uint32_t use[NB];
       for (int i = 0; i < NB; ++i) use[i] = 0;
-      for (int k = 1; k < p.ag.world; ++k) {
-        const int c = (p.ag.rank + k) % p.ag.world;
-        const char* src = reinterpret_cast<const char*>(p.ag.peer[c]);
-        char* dst = reinterpret_cast<char*>(p.ag.local) + static_cast<long long>(c) * chunk_bytes;
-        const long long n_sub = hi > lo ? (hi - lo + SUB - 1) / SUB : 0;
-        auto bytes_of = [&](long long i) {
-          const long long rem = hi - (lo + i * SUB);
-          return static_cast<uint32_t>(rem < static_cast<long long>(SUB) ? rem : static_cast<long long>(SUB));
-        };
-        long long issued = 0;
-        for (; issued < n_sub && issued < NB; ++issued) {
-          const int slot = static_cast<int>(issued % NB);
-          mbar_expect_tx(&pbar[slot], bytes_of(issued));
-          bulk_load_1d(smem + slot * SUB, src + lo + issued * SUB, bytes_of(issued), &pbar[slot]);
+      // Segments are visited in flat (address) order, interleaved over the copy-engine CTAs, so the first weight matrix of the
+      // unit — the one this very GEMM multiplies — lands first.  Every 16 KB piece goes peer HBM -> smem -> local HBM.
+      // Software pipeline: loads of segment k+1 are in flight while segment k is stored; flag k-1 is published once its
+      // bulk-store group has completed (groups retire in order).  Ring safety: before new loads are issued every earlier
+      // store has finished *reading* its slot (wait_group.read 0), and at most two segments (<= 10 of 12 slots) are live.
+      struct Piece { const char* src; char* dst; uint32_t bytes; };
+      auto pieces_of = [&](long long seg, Piece* pc) -> int {
+        const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
+        int n_p = 0;
+        for (long long e = e0; e < e1;) {
+          const int c = static_cast<int>(e / p.ag.chunk_elems);
+          const long long c_end = static_cast<long long>(c + 1) * p.ag.chunk_elems;
+          long long stop = e + SUB / 2;
+          if (stop > e1) stop = e1;
+          if (stop > c_end) stop = c_end;
+          if (c != p.ag.rank) {
+            pc[n_p].src = reinterpret_cast<const char*>(p.ag.peer[c]) + (e - static_cast<long long>(c) * p.ag.chunk_elems) * 2;
+            pc[n_p].dst = reinterpret_cast<char*>(p.ag.local) + e * 2;
+            pc[n_p].bytes = static_cast<uint32_t>((stop - e) * 2);
+            ++n_p;
+          }
+          e = stop;
         }
-        for (long long i = 0; i < n_sub; ++i) {
-          const int slot = static_cast<int>(i % NB);
+        return n_p;
+      };
+      auto next_remote = [&](long long seg) -> long long {      // first segment >= seg (in this CTA's stride) that is not entirely local
+        for (; seg < n_seg; seg += p.ag.n_ctas) {
+          const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
+          if (!(e0 >= loc0 && e1 <= loc1)) return seg;
+        }
+        return -1;
+      };
+      long long n_issued = 0, n_stored = 0;
+      auto issue_loads = [&](const Piece* pc, int n_p) {
+        for (int i = 0; i < n_p; ++i, ++n_issued) {
+          const int slot = static_cast<int>(n_issued % NB);
+          mbar_expect_tx(&pbar[slot], pc[i].bytes);
+          bulk_load_1d(smem + slot * SUB, pc[i].src, pc[i].bytes, &pbar[slot]);
+        }
+      };
+      Piece pcs[2][SUBS_PER_SEG + 2];
+      int npc[2];
+      long long cur = next_remote(blockIdx.x), prev = -1;
+      int cb = 0;
+      if (cur >= 0) { npc[0] = pieces_of(cur, pcs[0]); issue_loads(pcs[0], npc[0]); }
+      while (cur >= 0) {
+        const long long nxt = next_remote(cur + p.ag.n_ctas);
+        if (nxt >= 0) {
+          tma_wait_group_read<0>();                   // every earlier store has finished reading its ring slot (cheap: stores read smem in < 1 us)
+          npc[cb ^ 1] = pieces_of(nxt, pcs[cb ^ 1]);
+          issue_loads(pcs[cb ^ 1], npc[cb ^ 1]);
+        }
+        for (int i = 0; i < npc[cb]; ++i, ++n_stored) {
+          const int slot = static_cast<int>(n_stored % NB);
           mbar_wait(&pbar[slot], use[slot] & 1);
           use[slot]++;
-          bulk_store_1d(dst + lo + i * SUB, smem + slot * SUB, bytes_of(i));
-          tma_commit_group();
-          if (i >= 1 && issued < n_sub) {
-            tma_wait_group_read<1>();                       // the store that used slot (i-1) has finished reading smem
-            const int rs = static_cast<int>(issued % NB);   // == (i-1) % NB
-            mbar_expect_tx(&pbar[rs], bytes_of(issued));
-            bulk_load_1d(smem + rs * SUB, src + lo + issued * SUB, bytes_of(issued), &pbar[rs]);
-            ++issued;
-          }
+          bulk_store_1d(pcs[cb][i].dst, smem + slot * SUB, pcs[cb][i].bytes);
         }
-        tma_wait_group<0>();                                // all stores of this chunk slice are complete
+        tma_commit_group();                           // one bulk group per segment
+        if (prev >= 0) {
+          tma_wait_group<1>();                        // everything but the group just committed is complete -> `prev` has landed
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + prev), "r"(p.ag.target) : "memory");
+        }
+        prev = cur;
+        cur = nxt;
+        cb ^= 1;
+      }
+      tma_wait_group<0>();
+      if (prev >= 0) {
         asm volatile("fence.proxy.async.global;" ::: "memory");
-        __threadfence();
-        atomicAdd(p.ag.flags + c, 1u);
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + prev), "r"(p.ag.target) : "memory");
       }
     }
     // copy-engine CTAs own no GEMM tiles: fall through to the common teardown
@@ -177,7 +217,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int my_first_tile = tile0 >= 0 ? tile0 : num_tiles;
 
   // tile -> (m_blk, n_blk).  With a fused gather the n-blocks are rotated so that locally-owned weight rows come first.
-  const int n_rot = gather ? static_cast<int>(((static_cast<long long>(p.ag.rank) * p.ag.chunk_elems - p.ag.b_offset) / p.K) / BN) : 0;
+  const int n_rot = 0;   // segments land in address order, i.e. ascending weight rows: visit n-blocks in natural order
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
     const int per_group = GROUP_M * num_n;
     const int g = tile / per_group;
@@ -203,11 +243,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (gather) {
           const long long e0 = p.ag.b_offset + static_cast<long long>(n_blk) * BN * p.K;
           const long long rows = min(BN, p.N - n_blk * BN);
-          const long long e1 = e0 + rows * p.K - 1;
-          const int c0 = static_cast<int>(e0 / p.ag.chunk_elems), c1 = static_cast<int>(e1 / p.ag.chunk_elems);
-          for (int c = c0; c <= c1 && c < p.ag.world; ++c) {
-            if (c == p.ag.rank) continue;
-            while (ld_acquire_gpu_u32(p.ag.flags + c) < p.ag.target) {
+          const long long e1 = e0 + rows * p.K;
+          const long long loc0 = static_cast<long long>(p.ag.rank) * p.ag.chunk_elems, loc1 = loc0 + p.ag.chunk_elems;
+          for (long long sgm = e0 / SEG_ELEMS; sgm * SEG_ELEMS < e1; ++sgm) {
+            const long long s0 = sgm * SEG_ELEMS, s1 = s0 + SEG_ELEMS;
+            if (s0 >= loc0 && s1 <= loc1) continue;                 // locally owned rows
+            while (static_cast<int>(ld_acquire_gpu_u32(p.ag.flags + sgm) - p.ag.target) < 0) {
             }
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");

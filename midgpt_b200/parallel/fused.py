@@ -39,6 +39,7 @@ class GatherSpec:
 
 
 AG_CTAS = 12     # CTAs of the all-gather ⊕ GEMM grid that act as NVLink copy engines (12 x 16 KB bulk copies in flight each)
+SEG_ELEMS = 32768    # flag granularity (must match csrc/gemm.cu)
 
 
 class FusedComm:
@@ -91,8 +92,10 @@ class FusedComm:
             soff += u.shard
         if self.layer_mode:
             n_slots = len(engine._pool)
-            self.slot_flags = [torch.zeros(8, dtype=torch.int32, device=dev) for _ in range(n_slots)]
+            n_seg = max(u.padded for u in engine.units) // SEG_ELEMS + 2
+            self.slot_flags = [torch.zeros(n_seg, dtype=torch.int32, device=dev) for _ in range(n_slots)]
             self.slot_calls = [0] * n_slots
+            self._scratch_flags = torch.zeros(8, dtype=torch.int32, device=dev)     # stand-alone pulls are ordered by the stream
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._pushed = False
         self._barrier()          # every rank has zeroed / initialised its arenas
@@ -109,7 +112,7 @@ class FusedComm:
         """step mode: only the very first gather (initial weights) moves data; afterwards AdamW pushes keep lp_arena current.
         layer mode: stand-alone NVLink pull (used where no K-major GEMM is the first consumer, e.g. the embedding)."""
         if self.layer_mode:
-            self.ext.ag_pull(self._peer_shard_ptrs(u), u.lp_full, u.shard, self.rank, self._next_flags(u), AG_CTAS)
+            self.ext.ag_pull(self._peer_shard_ptrs(u), u.lp_full, u.shard, self.rank, self._scratch_flags, AG_CTAS)
             return
         if self._pushed:
             return
@@ -127,8 +130,7 @@ class FusedComm:
     def gather_spec(self, u) -> GatherSpec:
         """Descriptor consumed by the first K-major GEMM of the unit: that kernel performs the all-gather itself."""
         flags = self._next_flags(u)
-        return GatherSpec(self._peer_shard_ptrs(u), u.lp_full, flags, u.shard, self.slot_calls[u.pool_slot] * AG_CTAS,
-                          self.rank, AG_CTAS)
+        return GatherSpec(self._peer_shard_ptrs(u), u.lp_full, flags, u.shard, self.slot_calls[u.pool_slot], self.rank, AG_CTAS)
 
     def reduce_scatter(self, u) -> None:
         """Called on the comm stream once this rank's backward of unit ``u`` is complete."""

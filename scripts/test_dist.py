@@ -40,8 +40,8 @@ def main():
     x = torch.randn(M, K, device=dev).bfloat16()
     local_buf = torch.zeros(N * K, dtype=torch.bfloat16, device=dev)
     local_buf[rank * chunk:(rank + 1) * chunk].copy_(shard)
-    flags = torch.zeros(8, dtype=torch.int32, device=dev)
-    spec = GatherSpec([int(p) for p in h_shard.buffer_ptrs], local_buf, flags, chunk, AG_CTAS, rank, AG_CTAS)
+    flags = torch.zeros(4096, dtype=torch.int32, device=dev)
+    spec = GatherSpec([int(p) for p in h_shard.buffer_ptrs], local_buf, flags, chunk, 1, rank, AG_CTAS)
     y = be.linear_fwd(x, local_buf.view(N, K), gather=spec)
     ref = be.linear_fwd(x, w_full)
     err = ((y.float() - ref.float()).norm() / ref.float().norm()).item()
