@@ -16,6 +16,7 @@ void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb,
                      void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms,
                      cudaStream_t stream);
 void quant_rows_e4m3(const void* x, void* q, float* dequant, int R, int C, cudaStream_t s);
+void quant_mx_e4m3(const void* x, void* q, void* sf, int R, int C, cudaStream_t s);
 void rmsnorm_fwd(const void* x, void* y, float* rstd, int M, int D, float eps, cudaStream_t s);
 void rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* dres, void* dx, int M, int D, cudaStream_t s);
 void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const float* sin_t, const float* cos_t, void* qk,
@@ -124,6 +125,15 @@ std::vector<at::Tensor> quant_rows_e4m3(const at::Tensor& x) {
   auto dq = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
   mg::quant_rows_e4m3(x.data_ptr(), q.data_ptr(), dq.data_ptr<float>(), x.size(0), x.size(1), stream());
   return {q, dq};
+}
+// MX e4m3: returns (q uint8 [R,C], sf uint8 [ceil(R/128), C/128, 512]) — UE8M0 scale per 32 elements, tcgen05 atom order
+std::vector<at::Tensor> quant_mx_e4m3(const at::Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  CHECK_BF16(x); TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && x.size(1) % 128 == 0);
+  auto q = at::empty(x.sizes(), x.options().dtype(at::kByte));
+  auto sf = at::full({(x.size(0) + 127) / 128, x.size(1) / 128, 512}, 127, x.options().dtype(at::kByte));
+  mg::quant_mx_e4m3(x.data_ptr(), q.data_ptr(), sf.data_ptr(), x.size(0), x.size(1), stream());
+  return {q, sf};
 }
 // d = (a_q · b_qᵀ) ∘ (sa ⊗ sb) (+ epilogue), a_q [M,K] / b_q [N,K] e4m3 bytes
 void gemm_fp8(const at::Tensor& a, const at::Tensor& sa, const at::Tensor& b, const at::Tensor& sb, at::Tensor& d, int64_t epi,
@@ -304,6 +314,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM with fused epilogues");
   m.def("gemm_ag", &gemm_ag, "all-gather (NVLink pull) fused with the tcgen05 GEMM");
   m.def("quant_rows_e4m3", &quant_rows_e4m3);
+  m.def("quant_mx_e4m3", &quant_mx_e4m3);
   m.def("gemm_fp8", &gemm_fp8, "tcgen05 kind::f8f6f4 GEMM on row-scaled e4m3 operands");
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);

@@ -518,6 +518,65 @@ void quant_rows_e4m3(const void* x, void* q, float* dequant, int R, int C, cudaS
 }
 
 // ------------------------------------------------------------------------------------------------
+// MX (OCP micro-scaling) e4m3 quantisation: one UE8M0 scale per 32 consecutive elements of a row,
+//   scale = 2^ceil(log2(amax_block / 448)),  q = round_e4m3(x / scale).
+// Scales are written in the tcgen05 block-scale atom order: for every (128-row block, group of 4 k-blocks) a 512-byte
+// tile with byte offset (row%32)*16 + (row/32 %4)*4 + (kblock%4)  — the order tcgen05.cp.32x128b.warpx4 expects.
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256) quant_mx_e4m3_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q,
+                                                            uint8_t* __restrict__ sf, int R, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const int nvec = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(warp) * C);
+  uint2* qr = reinterpret_cast<uint2*>(q + static_cast<size_t>(warp) * C);
+  const int rb = warp >> 7, m = warp & 127, m0 = m & 31, m1 = m >> 5;
+  const size_t kgroups = static_cast<size_t>(C) >> 7;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;                 // 8-element vector index; 4 consecutive lanes = one 32-element block
+    float f[8];
+    float amax = 0.f;
+    if (j < nvec) {
+      unpack8(__ldg(xr + j), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(f[e]));
+    }
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    // exact ceil(log2(amax / 448)) from the float's exponent / mantissa (no transcendental approximations)
+    const uint32_t vb = __float_as_uint(fmaxf(amax, 1e-30f) * (1.f / 448.f));
+    int e8 = static_cast<int>((vb >> 23) & 0xFF) - 127 + ((vb & 0x7FFFFF) ? 1 : 0);
+    e8 = max(-127, min(127, e8));
+    const float inv = exp2f(static_cast<float>(-e8));
+    if (j < nvec) {
+      qr[j] = make_uint2(pack4_e4m3(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv), pack4_e4m3(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv));
+      if ((lane & 3) == 0) {
+        const int kblk = j >> 2;                 // 32-element block index along the row
+        sf[(static_cast<size_t>(rb) * kgroups + (kblk >> 2)) * 512 + m0 * 16 + m1 * 4 + (kblk & 3)] = static_cast<uint8_t>(e8 + 127);
+      }
+    }
+  }
+}
+void quant_mx_e4m3(const void* x, void* q, void* sf, int R, int C, cudaStream_t s) {
+  if (C % 128) throw std::runtime_error("quant_mx_e4m3: C must be a multiple of 128");
+  const int nvec = C / 8;
+  auto launch = [&](auto mv) {
+    constexpr int MAXV = decltype(mv)::value;
+    quant_mx_e4m3_kernel<MAXV><<<(R + 7) / 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), static_cast<uint8_t*>(sf), R, C);
+  };
+  if (nvec <= 32) launch(std::integral_constant<int, 1>());
+  else if (nvec <= 64) launch(std::integral_constant<int, 2>());
+  else if (nvec <= 128) launch(std::integral_constant<int, 4>());
+  else if (nvec <= 256) launch(std::integral_constant<int, 8>());
+  else if (nvec <= 512) launch(std::integral_constant<int, 16>());
+  else if (nvec <= 1024) launch(std::integral_constant<int, 32>());
+  else throw std::runtime_error("quant_mx_e4m3: row longer than 8192 elements");
+  check_launch("quant_mx_e4m3");
+}
+
+// ------------------------------------------------------------------------------------------------
 // Optimizer: Σ g² and the fused clip · Adam · independent-WD · LR · bf16 cast sweep over one fp32 shard
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ out) {

@@ -193,3 +193,22 @@ def test_fp8_quant_and_gemm(be):
     assert rel_err(y2, ref + res.float()) < 6e-3
     pre, act = be8.linear_fwd(x, w, act="gelu")
     assert rel_err(pre, ref) < 6e-3 and rel_err(act, torch.nn.functional.gelu(pre.float(), approximate="tanh")) < 6e-3
+
+
+def test_mx_quantisation_layout_and_values(be):
+    """MX e4m3: per-32-element UE8M0 scales in the tcgen05 scale-factor atom order; dequantised values match."""
+    torch.manual_seed(10)
+    R, C = 300, 512
+    x = rnd(R, C) * torch.exp(torch.randn(R, C // 32, device="cuda")).repeat_interleave(32, 1).bfloat16()
+    q, sf = be.ext.quant_mx_e4m3(x)
+    rows = torch.arange(R, device="cuda")
+    kb = torch.arange(C // 32, device="cuda")
+    rb, m = rows // 128, rows % 128
+    off = (m % 32) * 16 + (m // 32) * 4
+    idx = ((rb[:, None] * (C // 128) + (kb // 4)[None, :]) * 512 + off[:, None] + (kb % 4)[None, :])
+    e = sf.view(-1)[idx].float() - 127.0                       # [R, C/32] exponents
+    amax = x.float().abs().view(R, C // 32, 32).amax(-1)
+    want = torch.ceil(torch.log2(amax.clamp_min(1e-30) / 448.0)).clamp(-127, 127)
+    assert (e != want).float().mean().item() < 1e-3 and (e - want).abs().max().item() <= 1      # ties at exact powers of two aside
+    deq = q.view(torch.float8_e4m3fn).float().view(R, C // 32, 32) * torch.exp2(e)[..., None]
+    assert rel_err(deq.view(R, C), x) < 4e-2
