@@ -106,6 +106,18 @@ def main():
     target = max(fl / peak, by / NVLINK) * 1e3
     res.append({"kernel": "allgather_gemm_qkv", "ms": t, "gemm_only_ms": None, "target_ms": target, "frac_of_roofline": target / t,
                 "tflops": fl / t / 1e9, "nvlink_GBs_per_gpu": by / t / 1e6})
+    # pull-only sweeps: (a) the GEMM kernel's TMA copy engines with a negligible GEMM (M = 128), (b) the LSU pull kernel
+    xs = torch.randn(128, K, device=dev).bfloat16()
+    for n_ctas in (8, 16, 32, 64):
+        def pull_tma(n_ctas=n_ctas):
+            calls[0] += 1
+            spec = GatherSpec(sp, local, flags, shard, calls[0], rank, n_ctas)
+            be.linear_fwd(xs, local[: N * K].view(N, K), gather=spec)
+        tt = timeit(pull_tma, pre=barrier)
+        res.append({"kernel": f"ag_pull_tma_engines_{n_ctas}ctas", "ms": tt, "nvlink_GBs_per_gpu": by / tt / 1e6, "frac_of_770GBs": by / (tt * 1e-3) / NVLINK})
+        sflags = torch.zeros(8, dtype=torch.int32, device=dev)
+        tt = timeit(lambda n_ctas=n_ctas: ext.ag_pull(sp, local, shard, rank, sflags, n_ctas), pre=barrier)
+        res.append({"kernel": f"ag_pull_lsu_{n_ctas}ctas", "ms": tt, "nvlink_GBs_per_gpu": by / tt / 1e6, "frac_of_770GBs": by / (tt * 1e-3) / NVLINK})
     t_plain = timeit(lambda: be.linear_fwd(x, local[: N * K].view(N, K)))
     res[-1]["gemm_only_ms"] = t_plain
     def nccl_then_gemm():
