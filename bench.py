@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--gather-mode", default="auto")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--fp8", action="store_true", help="e4m3 forward GEMMs (separate config; the headline number is bf16)")
+    p.add_argument("--fp8-format", default="mx", choices=["mx", "row"])
     p.add_argument("--set", action="append", default=[])
     return p.parse_args()
 
@@ -140,6 +141,7 @@ def main():
     cfg.engine.gather_mode = args.gather_mode
     cfg.engine.micro_batch_size = args.micro_bs
     cfg.engine.fp8 = args.fp8
+    cfg.engine.fp8_format = args.fp8_format
     apply_overrides(cfg, args.set)
     T = cfg.model_config.block_size
     if args.remat == "auto":
@@ -223,7 +225,7 @@ def main():
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / PUBLISHED_TOKENS_PER_S if args.config == "openwebtext_xl" else None,
-            "dtype": "bf16" if not args.fp8 else "fp8-e4m3 forward GEMMs (row-scaled) / bf16 backward", "data": "synthetic tokens, random-init weights",
+            "dtype": "bf16" if not args.fp8 else f"fp8-e4m3 forward GEMMs ({'MX block-scaled' if args.fp8_format == 'mx' else 'row-scaled'}) / bf16 backward", "data": "synthetic tokens, random-init weights",
             "impl": "ours",
             "mfu_nominal_2.25PF": value * fpt / (2.25e15 * world),
             f"mfu_{how}_cublas_peak": value * fpt / (peak * world),

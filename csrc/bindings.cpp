@@ -15,6 +15,8 @@ void gemm_launch_ag_raw(const void* a, long long lda, const void* b, long long l
 void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb, const float* sa, const float* sb, void* d, long long ldd,
                      void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms,
                      cudaStream_t stream);
+void gemm_mx_launch(const void* a, const void* sfa, const void* b, const void* sfb, void* d, long long ldd, void* d2, long long ldd2,
+                    const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms, cudaStream_t stream);
 void quant_rows_e4m3(const void* x, void* q, float* dequant, int R, int C, cudaStream_t s);
 void quant_mx_e4m3(const void* x, void* q, void* sf, int R, int C, cudaStream_t s);
 void rmsnorm_fwd(const void* x, void* y, float* rstd, int M, int D, float eps, cudaStream_t s);
@@ -134,6 +136,23 @@ std::vector<at::Tensor> quant_mx_e4m3(const at::Tensor& x) {
   auto sf = at::full({(x.size(0) + 127) / 128, x.size(1) / 128, 512}, 127, x.options().dtype(at::kByte));
   mg::quant_mx_e4m3(x.data_ptr(), q.data_ptr(), sf.data_ptr(), x.size(0), x.size(1), stream());
   return {q, sf};
+}
+// MXFP8 block-scaled GEMM: d = dequant(a_q, sfa) · dequant(b_q, sfb)ᵀ, scales applied by tcgen05 block_scale MMAs
+void gemm_mx(const at::Tensor& a, const at::Tensor& sfa, const at::Tensor& b, const at::Tensor& sfb, at::Tensor& d, int64_t epi,
+             const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& aux) {
+  c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(a.scalar_type() == at::kByte && b.scalar_type() == at::kByte && a.is_contiguous() && b.is_contiguous());
+  TORCH_CHECK(sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte && sfa.is_contiguous() && sfb.is_contiguous());
+  CHECK_BF16(d); CHECK_2D_ROWMAJOR(d);
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K && d.size(0) == M && d.size(1) == N && d.stride(0) % 8 == 0);
+  TORCH_CHECK(sfa.numel() == ((M + 127) / 128) * (K / 128) * 512 && sfb.numel() == ((N + 127) / 128) * (K / 128) * 512, "gemm_mx: scale tensor size");
+  const void* auxp = nullptr; long long ld_aux = 0;
+  if (epi == 1) { TORCH_CHECK(aux.has_value()); CHECK_BF16(*aux); auxp = aux->data_ptr(); ld_aux = aux->stride(0); }
+  void* d2p = nullptr; long long ldd2 = 0;
+  if (epi == 2) { TORCH_CHECK(d2.has_value()); CHECK_BF16(*d2); d2p = d2->data_ptr(); ldd2 = d2->stride(0); }
+  mg::gemm_mx_launch(a.data_ptr(), sfa.data_ptr(), b.data_ptr(), sfb.data_ptr(), d.data_ptr(), d.stride(0), d2p, ldd2, auxp, ld_aux,
+                     static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), num_sms_of(a), stream());
 }
 // d = (a_q · b_qᵀ) ∘ (sa ⊗ sb) (+ epilogue), a_q [M,K] / b_q [N,K] e4m3 bytes
 void gemm_fp8(const at::Tensor& a, const at::Tensor& sa, const at::Tensor& b, const at::Tensor& sb, at::Tensor& d, int64_t epi,
@@ -315,6 +334,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_ag", &gemm_ag, "all-gather (NVLink pull) fused with the tcgen05 GEMM");
   m.def("quant_rows_e4m3", &quant_rows_e4m3);
   m.def("quant_mx_e4m3", &quant_mx_e4m3);
+  m.def("gemm_mx", &gemm_mx, "MXFP8 block-scaled GEMM (tcgen05 kind::mxf8f6f4.block_scale)");
   m.def("gemm_fp8", &gemm_fp8, "tcgen05 kind::f8f6f4 GEMM on row-scaled e4m3 operands");
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);

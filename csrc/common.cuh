@@ -47,6 +47,11 @@ MG_DEVICE float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+MG_DEVICE void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
 // tanh-GELU and its derivative (jax.nn.gelu(approximate=True), reference src/model.py:30)
 MG_DEVICE float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

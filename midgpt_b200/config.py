@@ -42,7 +42,8 @@ class EngineConfig:
     micro_batch_size: int = 0      # sequences per GPU per micro-step; 0 = choose automatically
     gather_mode: str = "auto"      # "step" (bf16 weights resident all step) | "layer" (gather per layer, free after use)
     prefetch_depth: int = 2        # units gathered ahead of the consumer when gather_mode == "layer"
-    fp8: bool = False              # forward GEMMs of the blocks in e4m3 (row-wise scaled, tcgen05 kind::f8f6f4); backward stays bf16
+    fp8: bool = False              # forward GEMMs of the blocks in e4m3 on the fp8 tensor cores; backward stays bf16
+    fp8_format: str = "mx"         # "mx": OCP MX block scaling (UE8M0 per 32 elements, tcgen05 block_scale) | "row": one fp32 scale per row
     cuda_graphs: bool = False
     seed: int = 0
     log_every: int = 20

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 
-def get_backend(name: str, device: torch.device, fp8: bool = False):
+def get_backend(name: str, device: torch.device, fp8: bool = False, fp8_format: str = "mx"):
     if name == "auto":
         name = "b200" if device.type == "cuda" else "torch"
     if name == "torch":
@@ -20,5 +20,5 @@ def get_backend(name: str, device: torch.device, fp8: bool = False):
         if device.type != "cuda":
             raise RuntimeError("backend 'b200' needs a CUDA (sm_100a) device")
         from .b200_backend import B200Backend
-        return B200Backend(device, fp8=fp8)
+        return B200Backend(device, fp8=fp8, fp8_format=fp8_format)
     raise ValueError(f"unknown backend {name!r}")

@@ -47,8 +47,9 @@ class QKV(tp.NamedTuple):
 class B200Backend:
     name = "b200"
 
-    def __init__(self, device: torch.device, fp8: bool = False):
-        self.fp8 = fp8
+    def __init__(self, device: torch.device, fp8: bool = False, fp8_format: str = "mx"):
+        assert fp8_format in ("mx", "row")
+        self.fp8, self.fp8_format = fp8, fp8_format
         self._wq: tp.Dict[int, tp.Tuple[int, torch.Tensor, torch.Tensor]] = {}
         self._wver = 0
         if device.type != "cuda":
@@ -114,20 +115,26 @@ class B200Backend:
         """Called by the engine after every optimizer step: cached e4m3 weights are stale."""
         self._wver += 1
 
-    def _quant_weight(self, w):
-        key = (w.data_ptr(), tuple(w.shape))
+    def _quant_weight(self, w, mx: bool):
+        key = (w.data_ptr(), tuple(w.shape), mx)
         hit = self._wq.get(key)
         if hit is None or hit[0] != self._wver:
-            q, s = self.ext.quant_rows_e4m3(w.contiguous())
+            q, s = (self.ext.quant_mx_e4m3 if mx else self.ext.quant_rows_e4m3)(w.contiguous())
             self.launches += 1
             hit = (self._wver, q, s)
             self._wq[key] = hit
         return hit[1], hit[2]
 
     def _linear_fwd_fp8(self, x, w, y, epi, d2=None, aux=None):
-        xq, sx = self.ext.quant_rows_e4m3(x)
-        wq, sw = self._quant_weight(w)
-        self.ext.gemm_fp8(xq, sx, wq, sw, y, epi, d2, aux)
+        mx = self.fp8_format == "mx" and w.shape[1] % 128 == 0
+        if mx:      # OCP MX: UE8M0 scale per 32 elements, applied inside tcgen05.mma.kind::mxf8f6f4.block_scale
+            xq, sx = self.ext.quant_mx_e4m3(x)
+            wq, sw = self._quant_weight(w, True)
+            self.ext.gemm_mx(xq, sx, wq, sw, y, epi, d2, aux)
+        else:       # one fp32 scale per row, applied in the epilogue of the kind::f8f6f4 GEMM
+            xq, sx = self.ext.quant_rows_e4m3(x)
+            wq, sw = self._quant_weight(w, False)
+            self.ext.gemm_fp8(xq, sx, wq, sw, y, epi, d2, aux)
         self.launches += 2
 
     # ---------------------------------------------------------------- linear

@@ -27,7 +27,7 @@ EXT_SUFFIX = sysconfig.get_config_var("EXT_SUFFIX")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "comm.cu"]
+CU_SOURCES = ["gemm.cu", "gemm_mx.cu", "elementwise.cu", "attention.cu", "comm.cu"]
 
 
 def _nvcc() -> str:

@@ -53,7 +53,7 @@ class Trainer:
         m = self.mesh
         if cfg.batch_size % m.world:
             raise ValueError(f"global batch_size {cfg.batch_size} not divisible by world size {m.world}")
-        self.backend = get_backend(cfg.engine.backend, m.device, fp8=cfg.engine.fp8)
+        self.backend = get_backend(cfg.engine.backend, m.device, fp8=cfg.engine.fp8, fp8_format=cfg.engine.fp8_format)
         self.engine = FSDPEngine(cfg, m, self.backend, seed=cfg.engine.seed)
         self.model = GPTModel(cfg.model_config, self.backend, remat=cfg.engine.remat, nvtx=cfg.debug)
         self.T = cfg.model_config.block_size

@@ -183,7 +183,7 @@ def test_fp8_quant_and_gemm(be):
     assert rel_err(deq, x) < 4e-2                       # e4m3 has 3 mantissa bits
     assert torch.allclose(s, x.float().abs().amax(1) / 448, rtol=1e-3)
     from midgpt_b200.ops.b200_backend import B200Backend
-    be8 = B200Backend(torch.device("cuda", 0), fp8=True)
+    be8 = B200Backend(torch.device("cuda", 0), fp8=True, fp8_format="row")
     wq, sw = be8.ext.quant_rows_e4m3(w)
     ref = (q.view(torch.float8_e4m3fn).float() * s[:, None]) @ (wq.view(torch.float8_e4m3fn).float() * sw[:, None]).t()
     y = be8.linear_fwd(x, w)
@@ -212,3 +212,32 @@ def test_mx_quantisation_layout_and_values(be):
     assert (e != want).float().mean().item() < 1e-3 and (e - want).abs().max().item() <= 1      # ties at exact powers of two aside
     deq = q.view(torch.float8_e4m3fn).float().view(R, C // 32, 32) * torch.exp2(e)[..., None]
     assert rel_err(deq.view(R, C), x) < 4e-2
+
+
+def _mx_dequant(q, sf, R, C):
+    rows = torch.arange(R, device="cuda")
+    kb = torch.arange(C // 32, device="cuda")
+    rb, m = rows // 128, rows % 128
+    off = (m % 32) * 16 + (m // 32) * 4
+    idx = ((rb[:, None] * (C // 128) + (kb // 4)[None, :]) * 512 + off[:, None] + (kb % 4)[None, :])
+    e = sf.view(-1)[idx].float() - 127.0
+    return (q.view(torch.float8_e4m3fn).float().view(R, C // 32, 32) * torch.exp2(e)[..., None]).view(R, C)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 128), (512, 768, 1024), (300, 2048, 2048)])
+def test_mxfp8_block_scaled_gemm(be, M, N, K):
+    """tcgen05 kind::mxf8f6f4.block_scale GEMM == fp32 matmul of the de-quantised MX operands."""
+    torch.manual_seed(11)
+    from midgpt_b200.ops.b200_backend import B200Backend
+    be8 = B200Backend(torch.device("cuda", 0), fp8=True, fp8_format="mx")
+    x = rnd(M, K) * torch.exp(0.5 * torch.randn(M, K // 32, device="cuda")).repeat_interleave(32, 1).bfloat16()
+    w, res = rnd(N, K, scale=K ** -0.5), rnd(M, N)
+    xq, sx = be8.ext.quant_mx_e4m3(x)
+    wq, sw = be8.ext.quant_mx_e4m3(w)
+    ref = _mx_dequant(xq, sx, M, K) @ _mx_dequant(wq, sw, N, K).t()
+    y = be8.linear_fwd(x, w)
+    assert rel_err(y, ref) < 6e-3
+    assert rel_err(y, x.float() @ w.float().t()) < 6e-2
+    assert rel_err(be8.linear_fwd(x, w, res=res), ref + res.float()) < 6e-3
+    pre, act = be8.linear_fwd(x, w, act="gelu")
+    assert rel_err(pre, ref) < 6e-3 and rel_err(act, torch.nn.functional.gelu(pre.float(), approximate="tanh")) < 6e-3
