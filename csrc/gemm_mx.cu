@@ -10,7 +10,8 @@
 // Structure = csrc/gemm.cu (TMA producer warp, single-thread MMA issuer, 8 epilogue warps, persistent M-grouped tiles) with:
 //   * 128 x 256 tiles, BK = 128 fp8 elements (128-byte swizzled rows), 4 stages of A 16 KB + B 32 KB + SFA 512 B + SFB 1 KB;
 //   * TMEM: accumulator 256 columns + 4 (SFA) + 8 (SFB) columns — the accumulator is single buffered (2 x 256 + 12 > 512),
-//     so the epilogue writes bf16 straight from registers to global memory (no staging, no barriers) to keep it short.
+//     so the epilogue first drains its 128 columns into registers, releases the accumulator at once, and then converts and
+//     writes bf16 straight to global memory while the next tile's MMAs already run.
 #include "common.cuh"
 
 #include <stdexcept>
@@ -178,11 +179,17 @@ gemm_mxfp8_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t t_row = tmem + (static_cast<uint32_t>(q * 32) << 16) + D_COL;
       const long long grow = static_cast<long long>(m_blk) * BM + row;
       const bool row_ok = grow < p.M;
-#pragma unroll 1
+      // Register-staged epilogue: this thread's 128 accumulator columns are pulled out of TMEM in one go and the (single)
+      // accumulator buffer is handed back to the MMA warp immediately; conversion and stores then overlap the next tile's MMAs.
+      uint32_t racc[BN / 64][32];
+#pragma unroll
+      for (int c = 0; c < BN / 64; ++c) tmem_ld_x32(t_row + c * 64 + half * 32, racc[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar);
+#pragma unroll
       for (int c = 0; c < BN / 64; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(t_row + c * 64 + half * 32, r);
-        tmem_ld_wait();
+        const uint32_t(&r)[32] = racc[c];
         const int col = n_blk * BN + c * 64 + half * 32;
         if (row_ok && col < p.N) {                             // N % 32 == 0 (host check): a 32-column slab is all-in or all-out
           __nv_bfloat16* dst = p.d + grow * p.ldd + col;
@@ -212,8 +219,6 @@ gemm_mxfp8_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar);
     }
   }
 
