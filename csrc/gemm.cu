@@ -64,6 +64,7 @@ struct GemmParams {
   int M, N, K;
   int accumulate;
   GatherParams ag;
+  int group_m;                      // rasterisation: m-blocks per group (groups sweep all n-blocks), chosen on the host
   const float* row_scale_a;         // FP8 only: de-quantisation multipliers, one per row of A (token) …
   const float* row_scale_b;         // … and one per row of B (output feature); acc[m,n] *= sa[m] * sb[n]
 };
@@ -172,10 +173,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // tile -> (m_blk, n_blk).  With a fused gather the n-blocks are rotated so that locally-owned weight rows come first.
   const int n_rot = 0;   // segments land in address order, i.e. ascending weight rows: visit n-blocks in natural order
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
-    const int per_group = GROUP_M * num_n;
+    const int per_group = p.group_m * num_n;
     const int g = tile / per_group;
-    const int first_m = g * GROUP_M;
-    const int gsize = min(num_m - first_m, GROUP_M);
+    const int first_m = g * p.group_m;
+    const int gsize = min(num_m - first_m, p.group_m);
     const int r = tile - g * per_group;
     m_blk = first_m + r % gsize;
     n_blk = r / gsize;
@@ -442,6 +443,17 @@ CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, long long rows, long l
   return m;
 }
 
+// One rasterisation group (group_m m-blocks x all n-blocks) should span about two waves of CTAs: every operand panel is then
+// shared by many concurrently running CTAs (L2 hits) and re-read from HBM as rarely as possible.  With few n-blocks (wgrad of
+// a narrow layer: N/256 = 8) the fixed group of 8 re-read the wide operand once per 64 tiles (ncu: 2x the ideal DRAM traffic).
+static int pick_group_m(int N, int num_sms) {
+  const int num_n = (N + BN - 1) / BN;
+  int g = (2 * num_sms + num_n - 1) / num_n;
+  if (g < GROUP_M) g = GROUP_M;
+  if (g > 64) g = 64;
+  return g;
+}
+
 template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false>
 static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tD2,
                        const GemmParams& p, int num_sms, cudaStream_t stream) {
@@ -496,7 +508,7 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
   CUtensorMap tB = b_mn ? make_tmap_2d(b, 2, K, N, ldb, 64, BK) : make_tmap_2d(b, 2, N, K, ldb, BK, BN);
   CUtensorMap tD = (epi == EPI_F32) ? make_tmap_2d(d, 4, M, N, ldd, 32, BM) : make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
-  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, nullptr, nullptr};
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, pick_group_m(N, num_sms), nullptr, nullptr};
   if (ag) {
     p.ag = *ag;
     if (a_mn || b_mn) throw std::runtime_error("all-gather ⊕ GEMM needs K-major operands");
@@ -531,7 +543,7 @@ void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb,
   CUtensorMap tB = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN);
   CUtensorMap tD = make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
-  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, sa, sb};
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, pick_group_m(N, num_sms), sa, sb};
   if (epi == EPI_STORE) return launch_one<false, false, EPI_STORE, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
   if (epi == EPI_GELU) return launch_one<false, false, EPI_GELU, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
   if (epi == EPI_RESIDUAL) return launch_one<false, false, EPI_RESIDUAL, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
