@@ -132,35 +132,51 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const long long loc0 = static_cast<long long>(p.ag.rank) * p.ag.chunk_elems, loc1 = loc0 + p.ag.chunk_elems;
     constexpr int V16 = static_cast<int>(SEG_ELEMS / 8);                  // uint4 per segment (4096)
     constexpr int PER_T = (V16 + NUM_THREADS - 1) / NUM_THREADS;          // 13
-    for (long long seg = blockIdx.x; seg < n_seg; seg += p.ag.n_ctas) {
+    // Two segments per round: 26 independent 16-byte peer loads in flight per thread (128 KB per CTA), then the stores, one
+    // fence + barrier, and the two release-flags.
+    auto seg_remote = [&](long long seg) {
       const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
-      if (e0 >= loc0 && e1 <= loc1) continue;                            // entirely local: consumers skip it too
-      uint4 v[PER_T];
-      bool live[PER_T];
+      return seg < n_seg && !(e0 >= loc0 && e1 <= loc1);
+    };
+    auto load_seg = [&](long long seg, uint4 (&v)[PER_T], uint32_t& live) {
+      const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
+      live = 0;
 #pragma unroll
       for (int u = 0; u < PER_T; ++u) {
         const long long e = e0 + (static_cast<long long>(u) * NUM_THREADS + threadIdx.x) * 8;
-        live[u] = false;
         if (e < e1) {
           const int c = static_cast<int>(e / p.ag.chunk_elems);          // chunk_elems is a multiple of 8: a uint4 never straddles
           if (c != p.ag.rank) {
             const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c]) +
                                                               (e - static_cast<long long>(c) * p.ag.chunk_elems));
             asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src));
-            live[u] = true;
+            live |= 1u << u;
           }
         }
       }
+    };
+    auto store_seg = [&](long long seg, const uint4 (&v)[PER_T], uint32_t live) {
+      const long long e0 = seg * SEG_ELEMS;
 #pragma unroll
-      for (int u = 0; u < PER_T; ++u) {
-        const long long e = e0 + (static_cast<long long>(u) * NUM_THREADS + threadIdx.x) * 8;
-        if (live[u]) *reinterpret_cast<uint4*>(p.ag.local + e) = v[u];
-      }
+      for (int u = 0; u < PER_T; ++u)
+        if (live & (1u << u)) *reinterpret_cast<uint4*>(p.ag.local + e0 + (static_cast<long long>(u) * NUM_THREADS + threadIdx.x) * 8) = v[u];
+    };
+    for (long long seg = blockIdx.x; seg < n_seg; seg += 2LL * p.ag.n_ctas) {
+      const long long sa = seg, sb = seg + p.ag.n_ctas;
+      const bool ra = seg_remote(sa), rb = seg_remote(sb);
+      if (!ra && !rb) continue;
+      uint4 va[PER_T], vb[PER_T];
+      uint32_t la = 0, lb = 0;
+      if (ra) load_seg(sa, va, la);
+      if (rb) load_seg(sb, vb, lb);
+      if (ra) store_seg(sa, va, la);
+      if (rb) store_seg(sb, vb, lb);
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.global;" ::: "memory");           // consumed by TMA (async proxy) in the GEMM CTAs
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + seg), "r"(p.ag.target) : "memory");
+        if (ra) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + sa), "r"(p.ag.target) : "memory");
+        if (rb) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + sb), "r"(p.ag.target) : "memory");
       }
     }
     // copy-engine CTAs own no GEMM tiles: fall through to the common teardown
