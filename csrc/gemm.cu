@@ -140,15 +140,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
     auto load_seg = [&](long long seg, uint4 (&v)[PER_T], uint32_t& live) {
       const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
+      // one 64-bit division per segment (not per load): a 64 KB segment touches at most two chunks
+      const int c0 = static_cast<int>(e0 / p.ag.chunk_elems);
+      const long long c0_end = static_cast<long long>(c0 + 1) * p.ag.chunk_elems;
+      const __nv_bfloat16* base0 = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c0]) - static_cast<long long>(c0) * p.ag.chunk_elems;
+      const int c1 = c0 + 1 < p.ag.world ? c0 + 1 : c0;
+      const __nv_bfloat16* base1 = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c1]) - static_cast<long long>(c1) * p.ag.chunk_elems;
       live = 0;
 #pragma unroll
       for (int u = 0; u < PER_T; ++u) {
         const long long e = e0 + (static_cast<long long>(u) * NUM_THREADS + threadIdx.x) * 8;
         if (e < e1) {
-          const int c = static_cast<int>(e / p.ag.chunk_elems);          // chunk_elems is a multiple of 8: a uint4 never straddles
+          const bool second = e >= c0_end;
+          const int c = second ? c1 : c0;
           if (c != p.ag.rank) {
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c]) +
-                                                              (e - static_cast<long long>(c) * p.ag.chunk_elems));
+            const uint4* src = reinterpret_cast<const uint4*>((second ? base1 : base0) + e);
             asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src));
             live |= 1u << u;
           }
@@ -528,6 +534,9 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
   if (ag) {
     p.ag = *ag;
     if (a_mn || b_mn) throw std::runtime_error("all-gather ⊕ GEMM needs K-major operands");
+    // weight rows arrive in address order: sweep all m-blocks of one n-block before the next n-block, so the first wave needs
+    // only the first 256 weight rows (1 MB) and later waves consume rows long after they landed; A stays L2-resident.
+    p.group_m = (M + BM - 1) / BM;
   }
   if (ag) {
     if (epi == EPI_STORE) return launch_one<false, false, EPI_STORE, true>(tA, tB, tD, tD2, p, num_sms, stream);

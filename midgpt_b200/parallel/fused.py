@@ -38,7 +38,7 @@ class GatherSpec:
         self.done = False
 
 
-AG_CTAS = 20     # CTAs of the all-gather ⊕ GEMM grid that act as NVLink copy engines (13 x 16 B loads in flight per thread)
+AG_CTAS = 24     # CTAs of the all-gather ⊕ GEMM grid that act as NVLink copy engines (13 x 16 B loads in flight per thread)
 SEG_ELEMS = 32768    # flag granularity (must match csrc/gemm.cu)
 
 
