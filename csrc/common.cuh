@@ -259,6 +259,47 @@ MG_DEVICE void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
 MG_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): cluster helpers, pair-wide TMEM allocation, TMA loads signalling the leader CTA's barrier,
+// M = 256 MMAs issued by the leader, multicast commits.  Building blocks verified by csrc/probe/cta2_probe.cu.
+// ------------------------------------------------------------------------------------------------
+MG_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+MG_DEVICE void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+MG_DEVICE uint32_t mapa_rank0(uint32_t smem_addr) {       // same offset in the leader CTA's shared window (cluster address)
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(0));
+  return r;
+}
+MG_DEVICE void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+template <uint32_t kCols>
+MG_DEVICE void tmem_alloc2(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+MG_DEVICE void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+MG_DEVICE void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+MG_DEVICE void umma_bf16_ss_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+MG_DEVICE void umma_commit_mc2(uint64_t* bar) {            // arrive on the barrier at this smem offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp in the vendored CUTLASS tree)
 // ------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle.

@@ -77,23 +77,31 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
 
 // FP8 = true: A and B hold e4m3 bytes (row-wise scaled, see quant_rows_e4m3 in elementwise.cu); the smem/TMA byte geometry
 // is unchanged (128-byte rows = 128 fp8 elements = one BK), tcgen05.mma runs kind::f8f6f4 with K = 32 per instruction.
-template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false>
+// CG2 = true: CTA-pair kernel (cluster 2x1x1, tcgen05 cta_group::2).  A pair owns a 256 x 256 output tile: each CTA loads its
+// 128 rows of A and HALF of the B tile (128 rows), the leader issues M = 256 MMAs that read both CTAs' smem, each CTA's TMEM
+// receives its 128 accumulator rows.  Per-SM smem traffic for B and the L2 -> SM traffic for B halve; 6 stages instead of 4.
+template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false, bool CG2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                   const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sC = smem + STAGES * STAGE_BYTES;
+  constexpr int NST = CG2 ? 6 : STAGES;                          // pipeline depth
+  constexpr int STG = CG2 ? 2 * A_STAGE_BYTES : STAGE_BYTES;     // bytes per stage in this CTA (A 16 KB + B 16 KB (half) | 32 KB)
+  static_assert(NST * STG == STAGES * STAGE_BYTES, "operand ring must end where the epilogue staging begins");
+  uint8_t* sC = smem + NST * STG;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + 2 * CSTAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + NST;
+  uint64_t* tfull_bar = empty_bar + NST;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
+  const int num_m = CG2 ? (p.M + 2 * BM - 1) / (2 * BM) : (p.M + BM - 1) / BM;   // CG2: tiles are 256 rows tall
+  const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   constexpr int BKE = FP8 ? 2 * BK : BK;            // elements per k-block (a k-block is always 128 bytes per row)
   const int num_k = (p.K + BKE - 1) / BKE;
@@ -103,19 +111,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
     if (EPI == EPI_GELU) tma_prefetch_desc(&tmD2);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], EPI_THREADS);
+      mbar_init(&tempty_bar[b], CG2 ? 2 * EPI_THREADS : EPI_THREADS);     // CG2: the leader waits for both CTAs' epilogues
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (CG2) tmem_alloc2<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG2) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -188,8 +200,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // copy-engine CTAs own no GEMM tiles: fall through to the common teardown
   }
   const int n_pull = gather ? p.ag.n_ctas : 0;
-  const int tile0 = static_cast<int>(blockIdx.x) - n_pull;              // negative for copy-engine CTAs -> no tiles
-  const int tile_stride = static_cast<int>(gridDim.x) - n_pull;
+  const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x) - n_pull;   // negative for copy-engine CTAs
+  const int tile_stride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x) - n_pull;
   const int my_first_tile = tile0 >= 0 ? tile0 : num_tiles;
 
   // tile -> (m_blk, n_blk).  With a fused gather the n-blocks are rotated so that locally-owned weight rows come first.
@@ -206,6 +218,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int rot = n_rot < 0 ? 0 : (n_rot >= num_n ? 0 : n_rot);
       n_blk = (n_blk + rot) % num_n;
     }
+    if (CG2) m_blk = 2 * m_blk + static_cast<int>(cta_rank);      // this CTA's 128-row block inside the pair's 256-row tile
   };
 
   if (warp == 0) {
@@ -231,31 +244,50 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sA = smem + stage * STG;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          if (!A_MN) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BKE, m_blk * BM);
-          } else {
+          if (CG2) {
+            // both CTAs load; every byte is credited to the LEADER's full barrier, which the leader arms for the pair's 64 KB
+            const uint32_t full_leader = mapa_rank0(smem_u32(&full_bar[stage]));
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STG);
+            const int b_row0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / 2);
+            if (!A_MN) {
+              tma_load_2d_cg2(sA, &tmA, full_leader, kb * BK, m_blk * BM);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
-          }
-          if (!B_MN) {
-            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BKE, n_blk * BN);
-          } else {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(sA + j * (BK * 128), &tmA, full_leader, m_blk * BM + j * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d_cg2(sB, &tmB, full_leader, kb * BK, b_row0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(sB + j * (BK * 128), &tmB, full_leader, b_row0 + j * 64, kb * BK);
+            }
+          } else {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(sA, &tmA, &full_bar[stage], kb * BKE, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d(sB, &tmB, &full_bar[stage], kb * BKE, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+            }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BM, BN) : make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    if (lane == 0 && (!CG2 || cta_rank == 0)) {           // CG2: only the leader CTA issues MMAs
+      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BM, BN) : make_idesc_bf16(CG2 ? 2 * BM : BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -268,7 +300,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t a_base = smem_u32(smem + stage * STG);
           const uint32_t b_base = a_base + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -277,12 +309,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, BK * 128, 1024)
                                      : make_smem_desc(b_base + k * 32, 16, 1024);
             if (FP8) umma_fp8_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else if (CG2) umma_bf16_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (CG2) umma_commit_mc2(&empty_bar[stage]);   // frees the smem slot in BOTH CTAs when these MMAs retire
+          else umma_commit(&empty_bar[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[buf]);        // accumulator complete -> epilogue
+        if (CG2) umma_commit_mc2(&tfull_bar[buf]);       // accumulator complete -> both CTAs' epilogues
+        else umma_commit(&tfull_bar[buf]);
       }
     }
   } else {
@@ -406,16 +441,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
-      // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
+      // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp (CG2: the leader's, remotely)
       tc_fence_before();
-      mbar_arrive(&tempty_bar[buf]);
+      if (CG2) mbar_arrive_cluster(mapa_rank0(smem_u32(&tempty_bar[buf])));
+      else mbar_arrive(&tempty_bar[buf]);
     }
     if (issuer) tma_wait_group<0>();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (CG2) cluster_sync();
+  if (warp == 1) {
+    if (CG2) tmem_dealloc2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -474,6 +514,41 @@ static int pick_group_m(int N, int num_sms) {
   if (g < GROUP_M) g = GROUP_M;
   if (g > 64) g = 64;
   return g;
+}
+
+static int g_use_cg2 = -1;      // CTA-pair kernels for the plain bf16 GEMMs (MIDGPT_GEMM_2CTA=0 disables)
+static bool use_cg2() {
+  if (g_use_cg2 < 0) {
+    const char* e = getenv("MIDGPT_GEMM_2CTA");
+    g_use_cg2 = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return g_use_cg2 == 1;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static void launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tD2,
+                        const GemmParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, false, false, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(pair): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
+  int pairs = num_sms / 2;
+  if (num_tiles < pairs) pairs = num_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA, tB, tD, tD2, p);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("gemm pair launch: ") + cudaGetErrorString(e));
 }
 
 template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false>
@@ -543,6 +618,24 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
     if (epi == EPI_GELU) return launch_one<false, false, EPI_GELU, true>(tA, tB, tD, tD2, p, num_sms, stream);
     if (epi == EPI_RESIDUAL) return launch_one<false, false, EPI_RESIDUAL, true>(tA, tB, tD, tD2, p, num_sms, stream);
     throw std::runtime_error("all-gather ⊕ GEMM: unsupported epilogue");
+  }
+  if (use_cg2() && M >= 2 * BM) {
+    // pair kernels: each CTA loads half of the B tile -> K-major B needs a 128-row box (MN-major boxes are 64 wide anyway)
+    CUtensorMap tB2 = b_mn ? tB : make_tmap_2d(b, 2, N, K, ldb, BK, BN / 2);
+    p.group_m = pick_group_m(N, num_sms / 2);
+#define MG_PAIR(AM, BM_, E) \
+    if (a_mn == AM && b_mn == BM_ && epi == E) return launch_pair<AM, BM_, E>(tA, tB2, tD, tD2, p, num_sms, stream);
+    MG_PAIR(false, false, EPI_STORE)
+    MG_PAIR(false, false, EPI_RESIDUAL)
+    MG_PAIR(false, false, EPI_GELU)
+    MG_PAIR(false, false, EPI_F32)
+    MG_PAIR(false, true, EPI_STORE)
+    MG_PAIR(false, true, EPI_DGELU)
+    MG_PAIR(false, true, EPI_RESIDUAL)
+    MG_PAIR(true, true, EPI_F32)
+    MG_PAIR(true, true, EPI_STORE)
+    MG_PAIR(true, false, EPI_F32)
+#undef MG_PAIR
   }
 #define MG_CASE(AM, BM_, E) \
   if (a_mn == AM && b_mn == BM_ && epi == E) return launch_one<AM, BM_, E>(tA, tB, tD, tD2, p, num_sms, stream);
