@@ -59,6 +59,21 @@ def main():
                           **{f"{a}_ms": round(b, 4) for a, b in rows.items()},
                           **{f"{a}_tflops": round(fl / b / 1e9, 1) for a, b in rows.items()},
                           "frac_of_%s_cublas_peak" % how: {a: round(fl / (b * 1e-3) / peak, 3) for a, b in rows.items() if "cublas" not in a}}), flush=True)
+    # FP8 forward GEMMs (quantisation of the activation included; weights are quantised once per optimizer step)
+    be_row, be_mx = B200Backend(dev, fp8=True, fp8_format="row"), B200Backend(dev, fp8=True, fp8_format="mx")
+    for name, m, n, k in shapes:
+        x, w = r(m, k), r(n, k) * k ** -0.5
+        fl = 2.0 * m * n * k
+        t_row = timeit(lambda: be_row.linear_fwd(x, w), flush=flush)
+        t_mx = timeit(lambda: be_mx.linear_fwd(x, w), flush=flush)
+        xq, sx = be_mx.ext.quant_mx_e4m3(x)
+        wq, sw = be_mx.ext.quant_mx_e4m3(w)
+        y = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+        t_mx_gemm = timeit(lambda: be_mx.ext.gemm_mx(xq, sx, wq, sw, y, 0, None, None), flush=flush)
+        print(json.dumps({"kernel": "gemm_fp8", "layer": name, "M": m, "N": n, "K": k, "row_scaled_fwd_ms": round(t_row, 4),
+                          "mx_fwd_ms": round(t_mx, 4), "mx_gemm_only_ms": round(t_mx_gemm, 4),
+                          "row_scaled_tflops": round(fl / t_row / 1e9, 1), "mx_tflops": round(fl / t_mx / 1e9, 1),
+                          "mx_gemm_only_tflops": round(fl / t_mx_gemm / 1e9, 1)}), flush=True)
     for (B, T, H, C) in ([(4, 1024, 16, 128)] if quick else [(16, 1024, 16, 128), (16, 1024, 12, 64), (4, 4096, 16, 128)]):
         D = H * C
         raw, qk = r(B * T, 3 * D), r(B * T, 2 * D)
