@@ -294,6 +294,11 @@ MG_DEVICE void umma_bf16_ss_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint3
                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
+MG_DEVICE void umma_fp8_ss_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
 MG_DEVICE void umma_commit_mc2(uint64_t* bar) {            // arrive on the barrier at this smem offset in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");

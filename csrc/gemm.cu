@@ -252,13 +252,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STG);
             const int b_row0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / 2);
             if (!A_MN) {
-              tma_load_2d_cg2(sA, &tmA, full_leader, kb * BK, m_blk * BM);
+              tma_load_2d_cg2(sA, &tmA, full_leader, kb * BKE, m_blk * BM);
             } else {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(sA + j * (BK * 128), &tmA, full_leader, m_blk * BM + j * 64, kb * BK);
             }
             if (!B_MN) {
-              tma_load_2d_cg2(sB, &tmB, full_leader, kb * BK, b_row0);
+              tma_load_2d_cg2(sB, &tmB, full_leader, kb * BKE, b_row0);
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(sB + j * (BK * 128), &tmB, full_leader, b_row0 + j * 64, kb * BK);
@@ -287,7 +287,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && (!CG2 || cta_rank == 0)) {           // CG2: only the leader CTA issues MMAs
-      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BM, BN) : make_idesc_bf16(CG2 ? 2 * BM : BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(CG2 ? 2 * BM : BM, BN) : make_idesc_bf16(CG2 ? 2 * BM : BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -308,7 +308,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                      : make_smem_desc(a_base + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, BK * 128, 1024)
                                      : make_smem_desc(b_base + k * 32, 16, 1024);
-            if (FP8) umma_fp8_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (FP8 && CG2) umma_fp8_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else if (FP8) umma_fp8_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             else if (CG2) umma_bf16_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -525,10 +526,10 @@ static bool use_cg2() {
   return g_use_cg2 == 1;
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, bool FP8 = false>
 static void launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tD2,
                         const GemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, false, false, true>;
+  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, false, FP8, true>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -662,6 +663,13 @@ void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb,
   CUtensorMap tD = make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
   GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, pick_group_m(N, num_sms), sa, sb};
+  if (use_cg2() && M >= 2 * BM) {
+    CUtensorMap tB2 = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN / 2);
+    p.group_m = pick_group_m(N, num_sms / 2);
+    if (epi == EPI_STORE) return launch_pair<false, false, EPI_STORE, true>(tA, tB2, tD, tD2, p, num_sms, stream);
+    if (epi == EPI_GELU) return launch_pair<false, false, EPI_GELU, true>(tA, tB2, tD, tD2, p, num_sms, stream);
+    if (epi == EPI_RESIDUAL) return launch_pair<false, false, EPI_RESIDUAL, true>(tA, tB2, tD, tD2, p, num_sms, stream);
+  }
   if (epi == EPI_STORE) return launch_one<false, false, EPI_STORE, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
   if (epi == EPI_GELU) return launch_one<false, false, EPI_GELU, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
   if (epi == EPI_RESIDUAL) return launch_one<false, false, EPI_RESIDUAL, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
