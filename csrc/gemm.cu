@@ -65,6 +65,7 @@ struct GemmParams {
   int accumulate;
   GatherParams ag;
   int group_m;                      // rasterisation: m-blocks per group (groups sweep all n-blocks), chosen on the host
+  int split_k;                      // > 1 only for the reduce-add fp32 epilogue (wgrad): K is cut into slices that add into D
   const float* row_scale_a;         // FP8 only: de-quantisation multipliers, one per row of A (token) …
   const float* row_scale_b;         // … and one per row of B (output feature); acc[m,n] *= sa[m] * sb[n]
 };
@@ -102,9 +103,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
   const int num_m = CG2 ? (p.M + 2 * BM - 1) / (2 * BM) : (p.M + BM - 1) / BM;   // CG2: tiles are 256 rows tall
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int tiles_mn = num_m * num_n;
+  const int num_tiles = tiles_mn * p.split_k;       // work items: (k-slice, tile), slice-major
   constexpr int BKE = FP8 ? 2 * BK : BK;            // elements per k-block (a k-block is always 128 bytes per row)
-  const int num_k = (p.K + BKE - 1) / BKE;
+  const int num_k_total = (p.K + BKE - 1) / BKE;
+  const int k_per_slice = (num_k_total + p.split_k - 1) / p.split_k;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -226,7 +229,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = my_first_tile; tile < num_tiles; tile += tile_stride) {
+      for (int item = my_first_tile; item < num_tiles; item += tile_stride) {
+        const int ks = item / tiles_mn, tile = item - ks * tiles_mn;
+        const int kb0 = ks * k_per_slice, kb1 = min(num_k_total, kb0 + k_per_slice);
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         if (gather) {
@@ -242,7 +247,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");
         }
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * STG;
           uint8_t* sB = sA + A_STAGE_BYTES;
@@ -291,13 +296,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = my_first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+      for (int item = my_first_tile; item < num_tiles; item += tile_stride, ++it) {
+        const int ks = item / tiles_mn;
+        const int kb0 = ks * k_per_slice, kb1 = min(num_k_total, kb0 + k_per_slice);
         const int buf = it & 1;
         const uint32_t tphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[buf], tphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * STG);
@@ -308,10 +315,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                      : make_smem_desc(a_base + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, BK * 128, 1024)
                                      : make_smem_desc(b_base + k * 32, 16, 1024);
-            if (FP8 && CG2) umma_fp8_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else if (FP8) umma_fp8_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else if (CG2) umma_bf16_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t acc = ((kb - kb0) | k) != 0 ? 1u : 0u;
+            if (FP8 && CG2) umma_fp8_ss_cg2(d_tmem, da, db, idesc, acc);
+            else if (FP8) umma_fp8_ss(d_tmem, da, db, idesc, acc);
+            else if (CG2) umma_bf16_ss_cg2(d_tmem, da, db, idesc, acc);
+            else umma_bf16_ss(d_tmem, da, db, idesc, acc);
           }
           if (CG2) umma_commit_mc2(&empty_bar[stage]);   // frees the smem slot in BOTH CTAs when these MMAs retire
           else umma_commit(&empty_bar[stage]);
@@ -329,7 +337,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool issuer = (threadIdx.x == 64);      // first epilogue thread issues the TMA stores
     const uint32_t sw = (row & 7);
     int it = 0;
-    for (int tile = my_first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+    for (int item = my_first_tile; item < num_tiles; item += tile_stride, ++it) {
+      const int tile = item % tiles_mn;
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int buf = it & 1;
@@ -517,6 +526,18 @@ static int pick_group_m(int N, int num_sms) {
   return g;
 }
 
+// Split-K for the accumulating fp32 epilogue (wgrad): the output has few tiles (e.g. 64–256 for the 1.5B layers) but K = #tokens is
+// huge, so whole waves are lost to quantisation; slices of K add into D with the same TMA reduce-add the epilogue uses anyway.
+static int pick_split_k(int tiles, int workers, int num_k, int epi, int accumulate) {
+  if (epi != EPI_F32 || !accumulate || tiles >= 8 * workers) return 1;
+  int s = (8 * workers + tiles - 1) / tiles;
+  const int max_s = num_k / 16 > 0 ? num_k / 16 : 1;     // keep >= 16 k-blocks (1024 tokens) per slice
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  const int kps = (num_k + s - 1) / s;          // k-blocks per slice as the kernel computes it …
+  return (num_k + kps - 1) / kps;               // … and the number of NON-EMPTY slices that yields
+}
+
 static int g_use_cg2 = -1;      // CTA-pair kernels for the plain bf16 GEMMs (MIDGPT_GEMM_2CTA=0 disables)
 static bool use_cg2() {
   if (g_use_cg2 < 0) {
@@ -536,7 +557,7 @@ static void launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUte
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(pair): ") + cudaGetErrorString(e));
     configured = true;
   }
-  const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
+  const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN) * p.split_k;
   int pairs = num_sms / 2;
   if (num_tiles < pairs) pairs = num_tiles;
   cudaLaunchConfig_t cfg{};
@@ -562,7 +583,7 @@ static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.split_k;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
   if (AG && p.ag.n_ctas > 0) {                      // copy-engine CTAs come on top of the GEMM workers (all co-resident: 1 CTA / SM)
     const int workers = num_tiles < num_sms - p.ag.n_ctas ? num_tiles : num_sms - p.ag.n_ctas;
@@ -606,7 +627,7 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
   CUtensorMap tB = b_mn ? make_tmap_2d(b, 2, K, N, ldb, 64, BK) : make_tmap_2d(b, 2, N, K, ldb, BK, BN);
   CUtensorMap tD = (epi == EPI_F32) ? make_tmap_2d(d, 4, M, N, ldd, 32, BM) : make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
-  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, pick_group_m(N, num_sms), nullptr, nullptr};
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, pick_group_m(N, num_sms), 1, nullptr, nullptr};
   if (ag) {
     p.ag = *ag;
     if (a_mn || b_mn) throw std::runtime_error("all-gather ⊕ GEMM needs K-major operands");
@@ -624,6 +645,7 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
     // pair kernels: each CTA loads half of the B tile -> K-major B needs a 128-row box (MN-major boxes are 64 wide anyway)
     CUtensorMap tB2 = b_mn ? tB : make_tmap_2d(b, 2, N, K, ldb, BK, BN / 2);
     p.group_m = pick_group_m(N, num_sms / 2);
+    p.split_k = pick_split_k(((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN), num_sms / 2, (K + BK - 1) / BK, epi, accumulate);
 #define MG_PAIR(AM, BM_, E) \
     if (a_mn == AM && b_mn == BM_ && epi == E) return launch_pair<AM, BM_, E>(tA, tB2, tD, tD2, p, num_sms, stream);
     MG_PAIR(false, false, EPI_STORE)
@@ -638,6 +660,7 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
     MG_PAIR(true, false, EPI_F32)
 #undef MG_PAIR
   }
+  p.split_k = pick_split_k(((M + BM - 1) / BM) * ((N + BN - 1) / BN), num_sms, (K + BK - 1) / BK, epi, accumulate);
 #define MG_CASE(AM, BM_, E) \
   if (a_mn == AM && b_mn == BM_ && epi == E) return launch_one<AM, BM_, E>(tA, tB, tD, tD2, p, num_sms, stream);
   MG_CASE(false, false, EPI_STORE)
@@ -662,7 +685,7 @@ void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb,
   CUtensorMap tB = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN);
   CUtensorMap tD = make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
-  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, pick_group_m(N, num_sms), sa, sb};
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, pick_group_m(N, num_sms), 1, sa, sb};
   if (use_cg2() && M >= 2 * BM) {
     CUtensorMap tB2 = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN / 2);
     p.group_m = pick_group_m(N, num_sms / 2);
