@@ -182,22 +182,30 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int u = 0; u < PER_T; ++u)
         if (live & (1u << u)) *reinterpret_cast<uint4*>(p.ag.local + e0 + (static_cast<long long>(u) * NUM_THREADS + threadIdx.x) * 8) = v[u];
     };
-    for (long long seg = blockIdx.x; seg < n_seg; seg += 2LL * p.ag.n_ctas) {
-      const long long sa = seg, sb = seg + p.ag.n_ctas;
-      const bool ra = seg_remote(sa), rb = seg_remote(sb);
-      if (!ra && !rb) continue;
-      uint4 va[PER_T], vb[PER_T];
-      uint32_t la = 0, lb = 0;
-      if (ra) load_seg(sa, va, la);
-      if (rb) load_seg(sb, vb, lb);
-      if (ra) store_seg(sa, va, la);
-      if (rb) store_seg(sb, vb, lb);
+    // One fence + barrier per ROUNDS rounds (8 segments): the block-wide fence costs several microseconds, the copies do not.
+    constexpr int ROUNDS = 4;
+    long long pend[2 * ROUNDS];
+    for (long long seg0 = blockIdx.x; seg0 < n_seg; seg0 += 2LL * ROUNDS * p.ag.n_ctas) {
+      int n_pend = 0;
+#pragma unroll 1
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        const long long sa = seg0 + 2LL * rd * p.ag.n_ctas, sb = sa + p.ag.n_ctas;
+        const bool ra = seg_remote(sa), rb = seg_remote(sb);
+        if (!ra && !rb) continue;
+        uint4 va[PER_T], vb[PER_T];
+        uint32_t la = 0, lb = 0;
+        if (ra) load_seg(sa, va, la);
+        if (rb) load_seg(sb, vb, lb);
+        if (ra) { store_seg(sa, va, la); pend[n_pend++] = sa; }
+        if (rb) { store_seg(sb, vb, lb); pend[n_pend++] = sb; }
+      }
+      if (n_pend == 0) continue;
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.global;" ::: "memory");           // consumed by TMA (async proxy) in the GEMM CTAs
-        if (ra) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + sa), "r"(p.ag.target) : "memory");
-        if (rb) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + sb), "r"(p.ag.target) : "memory");
+        for (int i = 0; i < n_pend; ++i)
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + pend[i]), "r"(p.ag.target) : "memory");
       }
     }
     // copy-engine CTAs own no GEMM tiles: fall through to the common teardown
