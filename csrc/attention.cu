@@ -567,6 +567,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
+      if (it > 0) {
+        // the previous tile's dQ reduce-add may still be reading its staging areas (the P/dS buffer and that tile's Q stage):
+        // wait for it only now, after this tile's exponentials have been computed, then release the Q/dO stage for refill
+        if (issuer) {
+          tma_wait_group_read<0>();
+          mbar_arrive(&qdo_empty[(it - 1) & 1]);     // second arrival (first: the MMA commit)
+        }
+        named_bar_sync(2, 256);
+      }
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint4 v4 = make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
@@ -628,12 +637,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh)
             tma_reduce_add_3d(&tmdQ, (rd == 0 ? sPS : stage_q) + hh * (128 * 128), h * C + hh * (C / 2) + rd * 32, q0, b);
-        tma_commit_group();
-        tma_wait_group_read<0>();
-        mbar_arrive(&qdo_empty[it & 1]);           // second arrival (first: the MMA commit) -> Q/dO stage may be refilled
+        tma_commit_group();                        // completion is awaited at the top of the next tile (overlaps its S wait + exps)
       }
-      named_bar_sync(2, 256);                      // staging areas reusable (next tile's P)
     }
+    if (issuer) tma_wait_group_read<0>();
     // ---- epilogue: dV, dK (thread = kv row x column half).  The last dq_full wait also covers the final dV/dK MMAs.
     const int kv_idx = kv0 + row;
     const bool kvalid = kv_idx < T;
