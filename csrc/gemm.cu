@@ -166,10 +166,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int u = 0; u < PER_T; ++u) {
         const long long e = e0 + (static_cast<long long>(u) * NUM_THREADS + threadIdx.x) * 8;
         if (e < e1) {
-          const bool second = e >= c0_end;
-          const int c = second ? c1 : c0;
+          bool second = e >= c0_end;
+          int c = second ? c1 : c0;
+          const __nv_bfloat16* base = second ? base1 : base0;
+          if (p.ag.chunk_elems < SEG_ELEMS) {        // tiny unit (e.g. a 65-token LM head): a segment may span > 2 chunks — exact, slow path
+            c = static_cast<int>(e / p.ag.chunk_elems);
+            base = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c]) - static_cast<long long>(c) * p.ag.chunk_elems;
+          }
           if (c != p.ag.rank) {
-            const uint4* src = reinterpret_cast<const uint4*>((second ? base1 : base0) + e);
+            const uint4* src = reinterpret_cast<const uint4*>(base + e);
             asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src));
             live |= 1u << u;
           }
