@@ -336,25 +336,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ================================================================================================
 // Backward
 // ================================================================================================
-// delta[b,h,t] = sum_c dO·O  (one warp per (token, head))
+// delta[b,h,t] = sum_c dO·O.  C/8 lanes per (token, head) vector with 16-byte loads; every lane keeps U vectors in
+// flight (2·U loads issued before any arithmetic) so the kernel runs at HBM speed instead of load latency.
+template <int C, int U>
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                                                            float* __restrict__ delta, int B, int T, int H, int C) {
-  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= static_cast<long long>(B) * T * H) return;
-  const int hh = w % H;
-  const long long bt = w / H;
-  const __nv_bfloat16* po = o + w * C;
-  const __nv_bfloat16* pd = dout + w * C;
-  float acc = 0.f;
-  for (int c = lane * 2; c < C; c += 64) {
-    float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(po + c));
-    float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(pd + c));
-    acc += a.x * d.x + a.y * d.y;
+                                                            float* __restrict__ delta, unsigned nvec, int T, int H) {
+  constexpr int LPV = C / 8, VPW = 32 / LPV;
+  const int lane = threadIdx.x & 31, sub = lane % LPV, slot = lane / LPV;
+  const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long base = static_cast<unsigned long long>(warp0) * (VPW * U); base < nvec;
+       base += static_cast<unsigned long long>(nwarps) * (VPW * U)) {
+    uint4 a[U], d[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long vec = base + u * VPW + slot;
+      const size_t v = vec < nvec ? vec : nvec - 1;
+      a[u] = __ldg(reinterpret_cast<const uint4*>(o + v * C) + sub);
+      d[u] = __ldg(reinterpret_cast<const uint4*>(dout + v * C) + sub);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t au[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, du[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = unpack_bf16(au[e]), y = unpack_bf16(du[e]);
+        acc += x.x * y.x + x.y * y.y;
+      }
+#pragma unroll
+      for (int off = LPV / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      const unsigned long long vec = base + u * VPW + slot;
+      if (sub == 0 && vec < nvec) {
+        const unsigned v = static_cast<unsigned>(vec);
+        const unsigned bt = v / H, hh = v - bt * H, bb = bt / T, t = bt - bb * T;
+        delta[(static_cast<size_t>(bb) * H + hh) * T + t] = acc;
+      }
+    }
   }
-  acc = warp_sum(acc);
-  const long long bb = bt / T, t = bt % T;
-  if (lane == 0) delta[(bb * H + hh) * T + t] = acc;
 }
 
 // dq (bf16, strided) = dq_accum (fp32 [M, D])
@@ -391,7 +409,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const __grid_constant__ CUtensorMap tmdQ, const float* __restrict__ lse, const float* __restrict__ delta,
                 __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long dkv_row_stride, int T, int H,
-                float scale) {
+                float scale, int dbg) {
+  // dbg (MIDGPT_ATTN_DEBUG, profiling experiments only; results are wrong when set): 1 = skip the dQ reduce-add,
+  // 2 = skip the exponentials, 4 = skip the dQ staging stores as well
   using Cfg = BwdCfg<C>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -551,7 +571,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_x32(t_lane + Cfg::S_COL + cbase, r0);
         tmem_ld_x32(t_lane + Cfg::S_COL + cbase + 32, r1);
         tmem_ld_wait();
-        if (!masked) {
+        if (dbg & 2) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { p[e] = __uint_as_float(r0[e]); p[32 + e] = __uint_as_float(r1[e]); }
+        } else if (!masked) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             p[e] = exp2f(fmaf(__uint_as_float(r0[e]), sl2, -lse2));
@@ -622,6 +645,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // staging: 32 fp32 columns per (column-half, round) = one [128 x 128 B] box; round 0 lives in the P/dS buffer, round 1
       // (C = 128 only) in this tile's Q stage, which the TMA producer may not refill before the drain has released it.
       uint8_t* stage_q = sQ + (it & 1) * Cfg::TILE;
+      if (!(dbg & 4))
 #pragma unroll
       for (int rd = 0; rd < ROUNDS; ++rd) {
         uint8_t* stg = (rd == 0 ? sPS : stage_q) + half * (128 * 128) + row * 128;
@@ -632,6 +656,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (issuer) {
+        if (!(dbg & 1))
 #pragma unroll
         for (int rd = 0; rd < ROUNDS; ++rd)
 #pragma unroll
@@ -716,23 +741,30 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
               void* dk, void* dv, float* dq_accum, int B, int T, int H, int C, long long q_row_stride, long long k_row_stride,
               long long v_row_stride, long long dqkv_row_stride, int num_sms, cudaStream_t s) {
   const float scale = 1.f / sqrtf(static_cast<float>(C));
-  const long long nwarp = static_cast<long long>(B) * T * H;
-  attn_bwd_prep_kernel<<<static_cast<unsigned>((nwarp + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, B, T, H, C);
+  const long long nvec = static_cast<long long>(B) * T * H;
+  if (nvec >= (1ll << 31)) throw std::runtime_error("attention: too many (token, head) vectors for 32-bit indexing");
+  if (C == 64)
+    attn_bwd_prep_kernel<64, 4><<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, static_cast<unsigned>(nvec), T, H);
+  else if (C == 128)
+    attn_bwd_prep_kernel<128, 4><<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, static_cast<unsigned>(nvec), T, H);
+  else
+    throw std::runtime_error("attention: head_dim must be 64 or 128");
   check("attn_bwd_prep");
   dim3 grid((T + 127) / 128, H, B);
   CUtensorMap tq = make_tmap_bthc(q, B, T, H, C, q_row_stride, 128), tk = make_tmap_bthc(k, B, T, H, C, k_row_stride, 128),
               tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, 128), tdo = make_tmap_bthc(dout, B, T, H, C, static_cast<long long>(H) * C, 128);
   CUtensorMap tdq = make_tmap_dq(dq_accum, B, T, H * C);
+  static const int dbg = [] { const char* e = getenv("MIDGPT_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
   if (C == 64) {
     static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
     (void)once;
     attn_bwd_kernel<64><<<grid, BwdCfg<64>::THREADS, BwdCfg<64>::SMEM, s>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk),
-                                                                             static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale);
+                                                                             static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale, dbg);
   } else if (C == 128) {
     static bool once = (set_smem(attn_bwd_kernel<128>, BwdCfg<128>::SMEM), true);
     (void)once;
     attn_bwd_kernel<128><<<grid, BwdCfg<128>::THREADS, BwdCfg<128>::SMEM, s>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk),
-                                                                               static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale);
+                                                                               static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale, dbg);
   } else {
     throw std::runtime_error("attention: head_dim must be 64 or 128");
   }

@@ -165,113 +165,144 @@ MG_DEVICE uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) qkln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ q_gain,
-                                                            const float* __restrict__ k_gain, const float* __restrict__ sin_t,
-                                                            const float* __restrict__ cos_t, __nv_bfloat16* __restrict__ qk,
-                                                            float* __restrict__ stats, long long nvec, int T, int H, float eps) {
+// Index algebra: vector v = m*2H + r with r = which*H + h, so the raw-projection offset is m*3HC + r*C and the output /
+// in-place offset math needs one 32-bit division per vector.  Every lane keeps U independent vectors in flight (all
+// global loads of a pass are issued before any arithmetic) -- with one vector per pass the kernels ran at ~45% of HBM
+// bandwidth purely on memory-level parallelism.
+template <int C, int U>
+__global__ void __launch_bounds__(256, 2) qkln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ q_gain,
+                                                               const float* __restrict__ k_gain, const float* __restrict__ sin_t,
+                                                               const float* __restrict__ cos_t, __nv_bfloat16* __restrict__ qk,
+                                                               float* __restrict__ stats, unsigned nvec, int T, int H, float eps) {
   constexpr int LPV = C / 8, VPW = 32 / LPV;
   const int lane = threadIdx.x & 31, sub = lane % LPV, slot = lane / LPV;
-  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned twoH = 2u * H;
   const int c0 = sub * 8;
   float gq[8], gk[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { gq[e] = q_gain[c0 + e]; gk[e] = k_gain[c0 + e]; }
-  for (long long base = warp0 * VPW; base < nvec; base += nwarps * VPW) {
-    const long long vec = base + slot;
-    const bool ok = vec < nvec;
-    const long long v = ok ? vec : nvec - 1;
-    const int h = v % H;
-    const int which = (v / H) & 1;          // 0 = q, 1 = k
-    const long long m = v / (2 * H);
-    const int pos = m % T;
-    float x[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + (m * 3 + which) * H * C + static_cast<long long>(h) * C + c0)), x);
-    float s = 0.f;
+  for (unsigned long long base = static_cast<unsigned long long>(warp0) * (VPW * U); base < nvec;
+       base += static_cast<unsigned long long>(nwarps) * (VPW * U)) {
+    uint4 raw[U];
+    unsigned vm[U], vr[U];
+    bool ok[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s += x[e];
-    const float mu = group_sum<LPV>(s) / C;
-    float ss = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { x[e] -= mu; ss += x[e] * x[e]; }
-    const float rs = rsqrtf(group_sum<LPV>(ss) / C + eps);
-    const float4 sn = __ldg(reinterpret_cast<const float4*>(sin_t + pos * (C / 2) + c0 / 2));
-    const float4 cs = __ldg(reinterpret_cast<const float4*>(cos_t + pos * (C / 2) + c0 / 2));
-    const float sv[4] = {sn.x, sn.y, sn.z, sn.w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
-    float o[8];
-#pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      const float a = x[e] * rs * (which ? gk[e] : gq[e]), b = x[e + 1] * rs * (which ? gk[e + 1] : gq[e + 1]);
-      o[e] = a * cv[e / 2] - b * sv[e / 2];
-      o[e + 1] = b * cv[e / 2] + a * sv[e / 2];
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long vec = base + u * VPW + slot;
+      ok[u] = vec < nvec;
+      const unsigned v = ok[u] ? static_cast<unsigned>(vec) : nvec - 1;
+      vm[u] = v / twoH;
+      vr[u] = v - vm[u] * twoH;
+      raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(vm[u]) * 3 * H + vr[u]) * C + c0));
     }
-    if (ok) {
-      *reinterpret_cast<uint4*>(qk + (m * 2 + which) * H * C + static_cast<long long>(h) * C + c0) = pack8(o);
-      if (sub == 0) *reinterpret_cast<float2*>(stats + vec * 2) = make_float2(mu, rs);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool which = vr[u] >= static_cast<unsigned>(H);   // false = q, true = k
+      const int pos = vm[u] % T;
+      float x[8];
+      unpack8(raw[u], x);
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += x[e];
+      const float mu = group_sum<LPV>(s) / C;
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { x[e] -= mu; ss += x[e] * x[e]; }
+      const float rs = rsqrtf(group_sum<LPV>(ss) / C + eps);
+      const float4 sn = __ldg(reinterpret_cast<const float4*>(sin_t + pos * (C / 2) + c0 / 2));
+      const float4 cs = __ldg(reinterpret_cast<const float4*>(cos_t + pos * (C / 2) + c0 / 2));
+      const float sv[4] = {sn.x, sn.y, sn.z, sn.w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const float a = x[e] * rs * (which ? gk[e] : gq[e]), b = x[e + 1] * rs * (which ? gk[e + 1] : gq[e + 1]);
+        o[e] = a * cv[e / 2] - b * sv[e / 2];
+        o[e + 1] = b * cv[e / 2] + a * sv[e / 2];
+      }
+      if (ok[u]) {
+        const size_t vec = static_cast<size_t>(vm[u]) * twoH + vr[u];
+        *reinterpret_cast<uint4*>(qk + vec * C + c0) = pack8(o);
+        if (sub == 0) *reinterpret_cast<float2*>(stats + vec * 2) = make_float2(mu, rs);
+      }
     }
   }
 }
 
 // In place on dqkv [M, 3, H, C] (q and k thirds): d(roped, normalised) -> d(raw projection output).
 // Gain gradients are accumulated per lane over the grid-stride loop, reduced through shared memory, then atomically added.
-template <int C>
-__global__ void __launch_bounds__(256) qkln_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, const __nv_bfloat16* __restrict__ qkv_raw,
-                                                            const float* __restrict__ stats, const float* __restrict__ q_gain,
-                                                            const float* __restrict__ k_gain, const float* __restrict__ sin_t,
-                                                            const float* __restrict__ cos_t, float* __restrict__ dq_gain,
-                                                            float* __restrict__ dk_gain, long long nvec, int T, int H) {
+template <int C, int U>
+__global__ void __launch_bounds__(256, 2) qkln_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, const __nv_bfloat16* __restrict__ qkv_raw,
+                                                               const float* __restrict__ stats, const float* __restrict__ q_gain,
+                                                               const float* __restrict__ k_gain, const float* __restrict__ sin_t,
+                                                               const float* __restrict__ cos_t, float* __restrict__ dq_gain,
+                                                               float* __restrict__ dk_gain, unsigned nvec, int T, int H) {
   constexpr int LPV = C / 8, VPW = 32 / LPV;
   __shared__ float red[2][C];
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) (&red[0][0])[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, sub = lane % LPV, slot = lane / LPV;
-  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned twoH = 2u * H;
   const int c0 = sub * 8;
   float gq[8], gk[8], gacc[2][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { gq[e] = q_gain[c0 + e]; gk[e] = k_gain[c0 + e]; gacc[0][e] = gacc[1][e] = 0.f; }
-  for (long long base = warp0 * VPW; base < nvec; base += nwarps * VPW) {
-    const long long vec = base + slot;
-    const bool ok = vec < nvec;
-    const long long v = ok ? vec : nvec - 1;
-    const int h = v % H;
-    const int which = (v / H) & 1;
-    const long long m = v / (2 * H);
-    const int pos = m % T;
-    const long long off = (m * 3 + which) * H * C + static_cast<long long>(h) * C + c0;
-    float g[8], x[8];
-    unpack8(*reinterpret_cast<const uint4*>(dqkv + off), g);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv_raw + off)), x);
-    const float2 st = __ldg(reinterpret_cast<const float2*>(stats + v * 2));
-    const float mu = st.x, rs = st.y;
-    const float4 sn = __ldg(reinterpret_cast<const float4*>(sin_t + pos * (C / 2) + c0 / 2));
-    const float4 cs = __ldg(reinterpret_cast<const float4*>(cos_t + pos * (C / 2) + c0 / 2));
-    const float sv[4] = {sn.x, sn.y, sn.z, sn.w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
-    float dxh[8], xh[8];
-    float s1 = 0.f, s2 = 0.f;
+  for (unsigned long long base = static_cast<unsigned long long>(warp0) * (VPW * U); base < nvec;
+       base += static_cast<unsigned long long>(nwarps) * (VPW * U)) {
+    uint4 graw[U], xraw[U];
+    float2 st[U];
+    unsigned vm[U], vr[U];
+    bool ok[U];
 #pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      const float dn0 = g[e] * cv[e / 2] + g[e + 1] * sv[e / 2];        // inverse rotation
-      const float dn1 = g[e + 1] * cv[e / 2] - g[e] * sv[e / 2];
-      xh[e] = (x[e] - mu) * rs;
-      xh[e + 1] = (x[e + 1] - mu) * rs;
-      if (ok) {
-        if (which) { gacc[1][e] += dn0 * xh[e]; gacc[1][e + 1] += dn1 * xh[e + 1]; }
-        else { gacc[0][e] += dn0 * xh[e]; gacc[0][e + 1] += dn1 * xh[e + 1]; }
-      }
-      dxh[e] = dn0 * (which ? gk[e] : gq[e]);
-      dxh[e + 1] = dn1 * (which ? gk[e + 1] : gq[e + 1]);
-      s1 += dxh[e] + dxh[e + 1];
-      s2 += dxh[e] * xh[e] + dxh[e + 1] * xh[e + 1];
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long vec = base + u * VPW + slot;
+      ok[u] = vec < nvec;
+      const unsigned v = ok[u] ? static_cast<unsigned>(vec) : nvec - 1;
+      vm[u] = v / twoH;
+      vr[u] = v - vm[u] * twoH;
+      const size_t off = (static_cast<size_t>(vm[u]) * 3 * H + vr[u]) * C + c0;
+      graw[u] = *reinterpret_cast<const uint4*>(dqkv + off);
+      xraw[u] = __ldg(reinterpret_cast<const uint4*>(qkv_raw + off));
+      st[u] = __ldg(reinterpret_cast<const float2*>(stats + static_cast<size_t>(v) * 2));
     }
-    s1 = group_sum<LPV>(s1) / C;
-    s2 = group_sum<LPV>(s2) / C;
-    float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = rs * (dxh[e] - s1 - xh[e] * s2);
-    if (ok) *reinterpret_cast<uint4*>(dqkv + off) = pack8(o);
+    for (int u = 0; u < U; ++u) {
+      const bool which = vr[u] >= static_cast<unsigned>(H);
+      const int pos = vm[u] % T;
+      float g[8], x[8];
+      unpack8(graw[u], g);
+      unpack8(xraw[u], x);
+      const float mu = st[u].x, rs = st[u].y;
+      const float4 sn = __ldg(reinterpret_cast<const float4*>(sin_t + pos * (C / 2) + c0 / 2));
+      const float4 cs = __ldg(reinterpret_cast<const float4*>(cos_t + pos * (C / 2) + c0 / 2));
+      const float sv[4] = {sn.x, sn.y, sn.z, sn.w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
+      float dxh[8], xh[8];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const float dn0 = g[e] * cv[e / 2] + g[e + 1] * sv[e / 2];        // inverse rotation
+        const float dn1 = g[e + 1] * cv[e / 2] - g[e] * sv[e / 2];
+        xh[e] = (x[e] - mu) * rs;
+        xh[e + 1] = (x[e + 1] - mu) * rs;
+        if (ok[u]) {
+          if (which) { gacc[1][e] += dn0 * xh[e]; gacc[1][e + 1] += dn1 * xh[e + 1]; }
+          else { gacc[0][e] += dn0 * xh[e]; gacc[0][e + 1] += dn1 * xh[e + 1]; }
+        }
+        dxh[e] = dn0 * (which ? gk[e] : gq[e]);
+        dxh[e + 1] = dn1 * (which ? gk[e + 1] : gq[e + 1]);
+        s1 += dxh[e] + dxh[e + 1];
+        s2 += dxh[e] * xh[e] + dxh[e + 1] * xh[e + 1];
+      }
+      s1 = group_sum<LPV>(s1) / C;
+      s2 = group_sum<LPV>(s2) / C;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rs * (dxh[e] - s1 - xh[e] * s2);
+      if (ok[u]) *reinterpret_cast<uint4*>(dqkv + (static_cast<size_t>(vm[u]) * 3 * H + vr[u]) * C + c0) = pack8(o);
+    }
   }
 #pragma unroll
   for (int w = 0; w < 2; ++w)
@@ -286,26 +317,30 @@ __global__ void __launch_bounds__(256) qkln_rope_bwd_kernel(__nv_bfloat16* __res
 
 void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const float* sin_t, const float* cos_t, void* qk,
                    float* stats, long long M, int T, int H, int C, float eps, cudaStream_t s) {
-  const long long nvec = M * 2 * H;
+  const long long nvec64 = M * 2 * H;
+  if (nvec64 >= (1ll << 31)) throw std::runtime_error("qkln_rope: too many (token, head) vectors for 32-bit indexing");
+  const unsigned nvec = static_cast<unsigned>(nvec64);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = static_cast<unsigned>(sms * 8);
+  const unsigned grid = static_cast<unsigned>(sms * 4);
   if (C == 64)
-    qkln_rope_fwd_kernel<64><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
+    qkln_rope_fwd_kernel<64, 4><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
   else if (C == 128)
-    qkln_rope_fwd_kernel<128><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
+    qkln_rope_fwd_kernel<128, 4><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), qg, kg, sin_t, cos_t, static_cast<__nv_bfloat16*>(qk), stats, nvec, T, H, eps);
   else throw std::runtime_error("qkln_rope: head_dim must be 64 or 128");
   check_launch("qkln_rope_fwd");
 }
 void qkln_rope_bwd(void* dqkv, const void* qkv_raw, const float* stats, const float* qg, const float* kg, const float* sin_t,
                    const float* cos_t, float* dqg, float* dkg, long long M, int T, int H, int C, int num_sms, cudaStream_t s) {
-  const long long nvec = M * 2 * H;
-  const unsigned grid = static_cast<unsigned>(num_sms * 8);
+  const long long nvec64 = M * 2 * H;
+  if (nvec64 >= (1ll << 31)) throw std::runtime_error("qkln_rope: too many (token, head) vectors for 32-bit indexing");
+  const unsigned nvec = static_cast<unsigned>(nvec64);
+  const unsigned grid = static_cast<unsigned>(num_sms * 4);
   if (C == 64)
-    qkln_rope_bwd_kernel<64><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
+    qkln_rope_bwd_kernel<64, 4><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
   else if (C == 128)
-    qkln_rope_bwd_kernel<128><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
+    qkln_rope_bwd_kernel<128, 4><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
   else throw std::runtime_error("qkln_rope: head_dim must be 64 or 128");
   check_launch("qkln_rope_bwd");
 }

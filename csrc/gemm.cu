@@ -66,6 +66,8 @@ struct GemmParams {
   GatherParams ag;
   int group_m;                      // rasterisation: m-blocks per group (groups sweep all n-blocks), chosen on the host
   int split_k;                      // > 1 only for the reduce-add fp32 epilogue (wgrad): K is cut into slices that add into D
+  __nv_bfloat16* d2;                // EPI_GELU: second output (gelu(pre)), written with direct 16-byte stores
+  long long ldd2;
   const float* row_scale_a;         // FP8 only: de-quantisation multipliers, one per row of A (token) …
   const float* row_scale_b;         // … and one per row of B (output feature); acc[m,n] *= sa[m] * sb[n]
 };
@@ -392,12 +394,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // 4 chunks of 64 bf16 columns (128 B per row); each warp of a pair converts 32 of them
 #pragma unroll 1
         for (int c = 0; c < BN / 64; ++c) {
-          uint8_t* sbuf = (EPI == EPI_GELU) ? sC : sC + (c & 1) * CSTAGE_BYTES;
-          uint8_t* sbuf2 = sC + CSTAGE_BYTES;
-          if (issuer) {
-            if (EPI == EPI_GELU) tma_wait_group_read<0>();
-            else tma_wait_group_read<1>();
-          }
+          uint8_t* sbuf = sC + (c & 1) * CSTAGE_BYTES;
+          if (issuer) tma_wait_group_read<1>();
           named_bar_sync(1, EPI_THREADS);
           uint32_t r[32];
           tmem_ld_x32(t_row + c * 64 + half * 32, r);
@@ -435,7 +433,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           } else {
-            uint8_t* rowp2 = sbuf2 + row * 128;
+            // GELU: the pre-activation goes through the staged TMA store, gelu(pre) straight from registers to global memory
+            // (64 contiguous bytes per thread) so the two staging buffers keep double-buffering the chunks
+            __nv_bfloat16* d2row = (EPI == EPI_GELU) ? p.d2 + grow * p.ldd2 + col0 + half * 32 : nullptr;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t o[4], g[4];
@@ -450,7 +450,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               }
               *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-              if (EPI == EPI_GELU) *reinterpret_cast<uint4*>(rowp2 + (((half * 4 + j) ^ sw) << 4)) = make_uint4(g[0], g[1], g[2], g[3]);
+              if (EPI == EPI_GELU && valid && col0 + half * 32 + 8 * j < p.N)
+                reinterpret_cast<uint4*>(d2row)[j] = make_uint4(g[0], g[1], g[2], g[3]);
             }
           }
           fence_proxy_async_smem();
@@ -458,7 +459,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (issuer) {
             if (col0 < p.N) {
               tma_store_2d(&tmD, sbuf, col0, m_blk * BM);
-              if (EPI == EPI_GELU) tma_store_2d(&tmD2, sbuf2, col0, m_blk * BM);
             }
             tma_commit_group();
           }
@@ -640,7 +640,7 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
   CUtensorMap tB = b_mn ? make_tmap_2d(b, 2, K, N, ldb, 64, BK) : make_tmap_2d(b, 2, N, K, ldb, BK, BN);
   CUtensorMap tD = (epi == EPI_F32) ? make_tmap_2d(d, 4, M, N, ldd, 32, BM) : make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
-  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, pick_group_m(N, num_sms), 1, nullptr, nullptr};
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, pick_group_m(N, num_sms), 1, static_cast<__nv_bfloat16*>(d2), ldd2, nullptr, nullptr};
   if (ag) {
     p.ag = *ag;
     if (a_mn || b_mn) throw std::runtime_error("all-gather ⊕ GEMM needs K-major operands");
@@ -698,7 +698,7 @@ void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb,
   CUtensorMap tB = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN);
   CUtensorMap tD = make_tmap_2d(d, 2, M, N, ldd, 64, BM);
   CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
-  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, pick_group_m(N, num_sms), 1, sa, sb};
+  GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, pick_group_m(N, num_sms), 1, static_cast<__nv_bfloat16*>(d2), ldd2, sa, sb};
   if (use_cg2() && M >= 2 * BM) {
     CUtensorMap tB2 = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN / 2);
     p.group_m = pick_group_m(N, num_sms / 2);
