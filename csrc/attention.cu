@@ -47,7 +47,7 @@ static CUtensorMap make_tmap_bthc(const void* ptr, int B, int T, int H, int C, l
 }
 
 // fp32 dQ accumulator [B, T, H*C] as a 3-D map so that query-tile rows past T are clipped instead of spilling into the next batch
-static CUtensorMap make_tmap_dq(const void* ptr, int B, int T, int D) {
+static CUtensorMap make_tmap_dq(const void* ptr, int B, int T, int D, int box_rows = 128) {
   cudaDriverEntryPointQueryResult q;
   void* p = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
@@ -56,7 +56,7 @@ static CUtensorMap make_tmap_dq(const void* ptr, int B, int T, int D) {
   CUtensorMap m;
   cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)D * 4 * T};
-  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -156,23 +156,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 5) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    // whole warp converged (descriptors stay in uniform registers), one elected lane per group of tcgen05 instructions
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, C, 0, 1);
-      const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
+      // descriptors are built once; per MMA only a 64-bit add of a compile-time offset (see desc_shift)
+      const uint64_t q_desc = make_smem_desc(smem_u32(sQ), 16, 1024), p_desc = make_smem_desc(smem_u32(sP), 16, 1024);
+      const uint64_t k_desc0 = make_smem_desc(smem_u32(sK), 16, 1024), v_desc0 = make_smem_desc(smem_u32(sV), BKV * 128, 1024);
       auto issue_qk = [&](int j) {
         const int st = j & 1;
         mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t k_base = smem_u32(sK + st * Cfg::K_BYTES);
+        const uint64_t k_desc = desc_shift(k_desc0, st * Cfg::K_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < C / 16; ++k) {
-          const uint32_t blk = (k * 16) / 64, in = (k * 16) % 64;
-          umma_bf16_ss(tmem + Cfg::S_COL + st * BKV, make_smem_desc(q_base + blk * (BQ * 128) + in * 2, 16, 1024),
-                       make_smem_desc(k_base + blk * (BKV * 128) + in * 2, 16, 1024), idesc_s, k != 0);
+          for (int k = 0; k < C / 16; ++k) {
+            const uint32_t blk = (k * 16) / 64, in = (k * 16) % 64;
+            umma_bf16_ss(tmem + Cfg::S_COL + st * BKV, desc_shift(q_desc, blk * (BQ * 128) + in * 2),
+                         desc_shift(k_desc, blk * (BKV * 128) + in * 2), idesc_s, k != 0);
+          }
+          umma_commit(&k_empty[st]);
+          umma_commit(&s_full[st]);
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[st]);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
@@ -183,15 +189,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int st = j & 1;
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_base = smem_u32(sV + st * Cfg::V_BYTES);
+        const uint64_t v_desc = desc_shift(v_desc0, st * Cfg::V_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint32_t blk = (k * 16) / 64, in = (k * 16) % 64;
-          umma_bf16_ss(tmem + Cfg::O_COL, make_smem_desc(p_base + blk * (BQ * 128) + in * 2, 16, 1024),
-                       make_smem_desc(v_base + k * 2048, BKV * 128, 1024), idesc_o, (j | k) != 0);
+          for (int k = 0; k < BKV / 16; ++k) {
+            const uint32_t blk = (k * 16) / 64, in = (k * 16) % 64;
+            umma_bf16_ss(tmem + Cfg::O_COL, desc_shift(p_desc, blk * (BQ * 128) + in * 2), desc_shift(v_desc, k * 2048), idesc_o, (j | k) != 0);
+          }
+          umma_commit(&v_empty[st]);
+          umma_commit(pv_done);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
+        __syncwarp();
         if (j + 2 < n_kv) issue_qk(j + 2);   // reuses S buffer j&1, which the softmax warps released at p_full(j)
       }
     }
@@ -340,7 +348,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // flight (2·U loads issued before any arithmetic) so the kernel runs at HBM speed instead of load latency.
 template <int C, int U>
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                                                            float* __restrict__ delta, unsigned nvec, int T, int H) {
+                                                            float* __restrict__ delta, const float* __restrict__ lse, float scale,
+                                                            size_t plane, unsigned nvec, int T, int H) {
+  // delta has three planes of `plane` = B*H*T floats: raw delta (v2 kernel) | delta*scale | lse*log2(e) (v3 kernel)
   constexpr int LPV = C / 8, VPW = 32 / LPV;
   const int lane = threadIdx.x & 31, sub = lane % LPV, slot = lane / LPV;
   const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -369,7 +379,10 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
       if (sub == 0 && vec < nvec) {
         const unsigned v = static_cast<unsigned>(vec);
         const unsigned bt = v / H, hh = v - bt * H, bb = bt / T, t = bt - bb * T;
-        delta[(static_cast<size_t>(bb) * H + hh) * T + t] = acc;
+        const size_t di = (static_cast<size_t>(bb) * H + hh) * T + t;
+        delta[di] = acc;
+        delta[plane + di] = acc * scale;
+        delta[2 * plane + di] = lse[di] * 1.4426950408889634f;
       }
     }
   }
@@ -479,34 +492,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 9) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    // whole warp converged (descriptors stay in uniform registers), one elected lane per group of tcgen05 instructions
+    {
       constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP : both operands K-major, N = 128
       constexpr uint32_t idesc_mm = make_idesc_bf16(128, C, 1, 1);     // dV, dK: both MN-major, N = C
       constexpr uint32_t idesc_km = make_idesc_bf16(128, C, 0, 1);     // dQ    : A K-major (dS), B MN-major (K)
-      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), ps_base = smem_u32(sPS);
+      // descriptors are built once; per MMA only a 64-bit add of a compile-time offset (see desc_shift)
+      const uint64_t k_k = make_smem_desc(smem_u32(sK), 16, 1024), v_k = make_smem_desc(smem_u32(sV), 16, 1024);       // K-major views
+      const uint64_t q_k0 = make_smem_desc(smem_u32(sQ), 16, 1024), do_k0 = make_smem_desc(smem_u32(sdO), 16, 1024);
+      const uint64_t k_mn = make_smem_desc(smem_u32(sK), 128 * 128, 1024), ps_mn = make_smem_desc(smem_u32(sPS), 128 * 128, 1024);   // MN-major views
+      const uint64_t q_mn0 = make_smem_desc(smem_u32(sQ), 128 * 128, 1024), do_mn0 = make_smem_desc(smem_u32(sdO), 128 * 128, 1024);
+      const uint64_t ps_k = make_smem_desc(smem_u32(sPS), 16, 1024);
       auto issue_s = [&](int it) {
         const int st = it & 1;
         mbar_wait(&q_full[st], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t q_base = smem_u32(sQ + st * Cfg::TILE);
+        const uint64_t q_k = desc_shift(q_k0, st * Cfg::TILE);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < C / 16; ++k) {
-          const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
-          umma_bf16_ss(tmem + Cfg::S_COL, make_smem_desc(q_base + off, 16, 1024), make_smem_desc(k_base + off, 16, 1024), idesc_kk, k != 0);
+          for (int k = 0; k < C / 16; ++k) {
+            const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
+            umma_bf16_ss(tmem + Cfg::S_COL, desc_shift(q_k, off), desc_shift(k_k, off), idesc_kk, k != 0);
+          }
+          umma_commit(s_full);
         }
-        umma_commit(s_full);
+        __syncwarp();
       };
       auto issue_dp = [&](int it) {
         const int st = it & 1;
         mbar_wait(&do_full[st], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t do_base = smem_u32(sdO + st * Cfg::TILE);
+        const uint64_t do_k = desc_shift(do_k0, st * Cfg::TILE);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < C / 16; ++k) {
-          const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
-          umma_bf16_ss(tmem + Cfg::DP_COL, make_smem_desc(do_base + off, 16, 1024), make_smem_desc(v_base + off, 16, 1024), idesc_kk, k != 0);
+          for (int k = 0; k < C / 16; ++k) {
+            const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
+            umma_bf16_ss(tmem + Cfg::DP_COL, desc_shift(do_k, off), desc_shift(v_k, off), idesc_kk, k != 0);
+          }
+          umma_commit(dp_full);
         }
-        umma_commit(dp_full);
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
       issue_s(0);
@@ -514,29 +539,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int it = 0; it < n_it; ++it) {
         const uint32_t ph = it & 1;
         const int st = it & 1;
-        const uint32_t q_base = smem_u32(sQ + st * Cfg::TILE), do_base = smem_u32(sdO + st * Cfg::TILE);
+        const uint64_t q_mn = desc_shift(q_mn0, st * Cfg::TILE), do_mn = desc_shift(do_mn0, st * Cfg::TILE);
         // dV += Pᵀ · dO        (A = P as MN-major [k = q rows][m = kv], B = dO as MN-major [k = q rows][n = c])
         mbar_wait(p_ready, ph);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16_ss(tmem + Cfg::DV_COL, make_smem_desc(ps_base + k * 2048, 128 * 128, 1024),
-                       make_smem_desc(do_base + k * 2048, 128 * 128, 1024), idesc_mm, (it | k) != 0);
-        umma_commit(dv_done);
+          for (int k = 0; k < 128 / 16; ++k)
+            umma_bf16_ss(tmem + Cfg::DV_COL, desc_shift(ps_mn, k * 2048), desc_shift(do_mn, k * 2048), idesc_mm, (it | k) != 0);
+          umma_commit(dv_done);
+        }
+        __syncwarp();
         // dK += dSᵀ · Q ; dQ = dS · K   (dS overwrote P in the same buffer)
         mbar_wait(ds_ready, ph);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16_ss(tmem + Cfg::DK_COL, make_smem_desc(ps_base + k * 2048, 128 * 128, 1024),
-                       make_smem_desc(q_base + k * 2048, 128 * 128, 1024), idesc_mm, (it | k) != 0);
+          for (int k = 0; k < 128 / 16; ++k)
+            umma_bf16_ss(tmem + Cfg::DK_COL, desc_shift(ps_mn, k * 2048), desc_shift(q_mn, k * 2048), idesc_mm, (it | k) != 0);
 #pragma unroll
-        for (int k = 0; k < 128 / 16; ++k) {
-          const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
-          umma_bf16_ss(tmem + Cfg::DP_COL, make_smem_desc(ps_base + off, 16, 1024), make_smem_desc(k_base + k * 2048, 128 * 128, 1024), idesc_km, k != 0);
+          for (int k = 0; k < 128 / 16; ++k) {
+            const uint32_t off = ((k * 16) / 64) * (128 * 128) + ((k * 16) % 64) * 2;
+            umma_bf16_ss(tmem + Cfg::DP_COL, desc_shift(ps_k, off), desc_shift(k_mn, k * 2048), idesc_km, k != 0);
+          }
+          umma_commit(&qdo_empty[st]);
+          umma_commit(dq_full);
         }
-        umma_commit(&qdo_empty[st]);
-        umma_commit(dq_full);
+        __syncwarp();
         if (it + 1 < n_it) {
           issue_s(it + 1);                       // S columns were released at p_ready(it)
           mbar_wait(dq_drained, ph);             // dQ(it) read out -> dP columns reusable
@@ -701,6 +730,367 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ================================================================================================
+// Backward, version 3 (head_dim 128, T % 64 == 0): transposed scores, P/dS kept in tensor memory, 64-row query tiles.
+//
+//   One CTA = one (batch, head, 128-key tile); loop over 64-row query tiles at or below the diagonal.
+//   Sᵀ = K·Qᵀ and dPᵀ = V·dOᵀ put KEYS on the TMEM lanes, so Pᵀ and dSᵀ (bf16, packed two per column, written back over
+//   the fp32 columns they came from with tcgen05.st) are directly the A operands of dV += Pᵀ·dO and dK += dSᵀ·Q
+//   (tcgen05.mma with A in TMEM): no P tile in shared memory, half the operand traffic for those two products.
+//   dQᵀ = Kᵀ·dS (M = head_dim, N = 64 queries) has its OWN 64 TMEM columns and dPᵀ is double buffered, so nothing in a tile
+//   aliases the next one.  Tensor-pipe order:  dV(i) | S(i+1) dP(i+1) | dK(i) dQ(i): the next tile's scores and dP are in
+//   TMEM before the softmax warps finish dS(i), so their loop P(i) → dS(i) → P(i+1) never waits for the tensor core, and
+//   the dQ(i) drain (transposing staging store + TMA reduce-add, double buffered) runs on four dedicated warps one tile
+//   behind.  Version 2 (above in the file, still used for head_dim 64 / ragged T) had to walk each tile in lock step
+//   because dQ aliased dP and P, dS and the dQ staging shared one buffer.
+//
+//   TMEM columns:  Sᵀ 0..63 (Pᵀ packed in the first 16 columns of each 32-column half) | dPᵀ[2] 64..191 (dSᵀ packed
+//   likewise) | dQᵀ 192..255 | dV 256..383 | dK 384..511
+//   warps 0-7 softmax (thread = key row × 32-query half), 8-11 dQ drain, 12 TMA producer, 13 MMA issuer.
+// ================================================================================================
+struct Bwd3Cfg {
+  static constexpr int C = 128, BQ = 64;
+  static constexpr int KV_TILE = 128 * C * 2;          // K or V   [128 x C] bf16
+  static constexpr int Q_TILE = BQ * C * 2;            // Q or dO  [64 x C] bf16
+  static constexpr int NQ = 3, NDO = 2;                // pipeline depth of the Q and dO stages
+  static constexpr int DS = 128 * BQ * 2;              // dSᵀ [128 keys x 64 queries] bf16 (B operand of the dQᵀ product)
+  static constexpr int STG = BQ * C * 4;               // dQ staging [64 queries x C] fp32, 2 buffers
+  static constexpr int STAT = 2 * BQ * 4;              // lse·log2e | delta·scale of one query tile
+  static constexpr int SMEM = 2 * KV_TILE + (NQ + NDO) * Q_TILE + DS + 2 * STG + NQ * STAT + 256;
+  static constexpr int ST_COL = 0, DPT_COL = 64, DQT_COL = 192, DV_COL = 256, DK_COL = 384;   // dPᵀ: 2 buffers of 64 columns
+  static constexpr int NSW = 8, NDW = 4;               // softmax warps (P, dS, final dV/dK epilogue), dQ drain warps
+  static constexpr int NST = 32 * NSW, NDT = 32 * NDW;
+  static constexpr int THREADS = NST + NDT + 64;       // + TMA warp + MMA warp
+  static constexpr int CPT = 64 * 4 / NSW;             // query columns per softmax thread: 4 lane quarters x 2 column groups
+};
+
+__global__ void __launch_bounds__(Bwd3Cfg::THREADS, 1)
+attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                 const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
+                 const __grid_constant__ CUtensorMap tmdV, const float* __restrict__ lse2, const float* __restrict__ dsc,
+                 int T, int H, float scale, int dbg) {
+  using Cfg = Bwd3Cfg;
+  constexpr int C = Cfg::C, CPT = Cfg::CPT;
+  constexpr int W_DRAIN = Cfg::NSW, W_TMA = Cfg::NSW + Cfg::NDW, W_MMA = W_TMA + 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + Cfg::KV_TILE;
+  uint8_t* sQ = sV + Cfg::KV_TILE;                       // NQ stages; reused as the dV output tile at the end
+  uint8_t* sdO = sQ + Cfg::NQ * Cfg::Q_TILE;             // NDO stages; reused as the dK output tile at the end
+  uint8_t* sDS = sdO + Cfg::NDO * Cfg::Q_TILE;
+  uint8_t* sStg = sDS + Cfg::DS;                         // 2 buffers
+  uint8_t* sStat = sStg + 2 * Cfg::STG;                  // NQ x (lse2[64] | dsc[64])
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + Cfg::NQ * Cfg::STAT);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;       // [3] Q tile + its statistics landed
+  uint64_t* q_empty = bars + 4;      // [3] dK(i) retired: Q stage (and its statistics) reusable
+  uint64_t* do_full = bars + 7;      // [2]
+  uint64_t* do_empty = bars + 9;     // [2] dV(i) retired
+  uint64_t* s_full = bars + 11;
+  uint64_t* dp_full = bars + 12;     // [2] dPᵀ(i) retired (buffer i & 1)
+  uint64_t* p_ready = bars + 14;     // NST arrivals: Pᵀ(i) in TMEM
+  uint64_t* ds_ready = bars + 15;    // NST arrivals: dSᵀ(i) in TMEM and in shared memory
+  uint64_t* dq_full = bars + 16;     // dQᵀ(i) (and everything issued before it) retired
+  uint64_t* dq_drained = bars + 17;  // NDT arrivals: dQᵀ(i) read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kv0 = jt * 128;
+  const int n_it = T / 64 - 2 * jt;                // query tiles kv0/64 .. T/64-1
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
+    tma_prefetch_desc(&tmdK); tma_prefetch_desc(&tmdV);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 3; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&do_full[s], 1); mbar_init(&do_empty[s], 1); mbar_init(&dp_full[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, Cfg::NST); mbar_init(ds_ready, Cfg::NST); mbar_init(dq_full, 1); mbar_init(dq_drained, Cfg::NDT);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long long stat_row = (static_cast<long long>(b) * H + h) * T;
+
+  if (warp == W_TMA) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * Cfg::KV_TILE);
+#pragma unroll
+      for (int cb = 0; cb < C / 64; ++cb) {
+        tma_load_4d(sK + cb * (128 * 128), &tmK, kv_full, cb * 64, h, kv0, b);
+        tma_load_4d(sV + cb * (128 * 128), &tmV, kv_full, cb * 64, h, kv0, b);
+      }
+      int s = 0;
+      uint32_t qph = 0;
+      for (int it = 0; it < n_it; ++it) {
+        const int q0 = kv0 + it * 64;
+        mbar_wait(&q_empty[s], qph ^ 1);
+        mbar_expect_tx(&q_full[s], Cfg::Q_TILE + Cfg::STAT);
+#pragma unroll
+        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sQ + s * Cfg::Q_TILE + cb * (64 * 128), &tmQ, &q_full[s], cb * 64, h, q0, b);
+        bulk_load_1d(sStat + s * Cfg::STAT, lse2 + stat_row + q0, 256, &q_full[s]);
+        bulk_load_1d(sStat + s * Cfg::STAT + 256, dsc + stat_row + q0, 256, &q_full[s]);
+        const int d = it & 1;
+        mbar_wait(&do_empty[d], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&do_full[d], Cfg::Q_TILE);
+#pragma unroll
+        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sdO + d * Cfg::Q_TILE + cb * (64 * 128), &tmdO, &do_full[d], cb * 64, h, q0, b);
+        if (++s == 3) { s = 0; qph ^= 1; }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ------------------------------- MMA issuer -------------------------------
+    // The whole warp runs this (converged) control flow so that descriptors and addresses live in uniform registers; one
+    // elected lane issues each group of tcgen05 instructions.  With `if (lane == 0)` around everything the compiler wraps
+    // every MMA in a register->uniform-register waterfall loop and the issuing thread, not the tensor core, sets the pace.
+    {
+      constexpr uint32_t idesc_st = make_idesc_bf16(128, 64, 0, 0);    // Sᵀ, dPᵀ: A = K / V (K-major), B = Q / dO (K-major), N = 64
+      constexpr uint32_t idesc_ts = make_idesc_bf16(128, C, 0, 1);     // dV, dK : A in TMEM, B = dO / Q MN-major, N = C
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);    // dQᵀ    : A = Kᵀ (MN-major), B = dSᵀ tile (MN-major), N = 64
+      // descriptors are built once; per MMA only a 64-bit add of a compile-time offset (see desc_shift)
+      const uint64_t k_k = make_smem_desc(smem_u32(sK), 16, 1024), v_k = make_smem_desc(smem_u32(sV), 16, 1024);       // K-major views
+      const uint64_t q_k0 = make_smem_desc(smem_u32(sQ), 16, 1024), do_k0 = make_smem_desc(smem_u32(sdO), 16, 1024);
+      const uint64_t k_mn = make_smem_desc(smem_u32(sK), 128 * 128, 1024), ds_mn = make_smem_desc(smem_u32(sDS), 64 * 128, 1024);   // MN-major views
+      const uint64_t q_mn0 = make_smem_desc(smem_u32(sQ), 64 * 128, 1024), do_mn0 = make_smem_desc(smem_u32(sdO), 64 * 128, 1024);
+      // column of k-step ks (queries 16·ks ..) of a packed Pᵀ/dSᵀ operand: every thread packs its CPT columns into the first
+      // CPT/2 columns of its own CPT-column group
+      auto a_col = [](int ks) { return ((16 * ks) / CPT) * CPT + ((16 * ks) % CPT) / 2; };
+      auto issue_st = [&](uint32_t d_col, uint64_t a_desc, uint64_t b_desc, uint64_t* bar) {
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < C / 16; ++k) {
+            const uint32_t offa = (k / 4) * (128 * 128) + (k % 4) * 32, offb = (k / 4) * (64 * 128) + (k % 4) * 32;
+            umma_bf16_ss(tmem + d_col, desc_shift(a_desc, offa), desc_shift(b_desc, offb), idesc_st, k != 0);
+          }
+          umma_commit(bar);
+        }
+        __syncwarp();
+      };
+      auto issue_s = [&](int it, int s, uint32_t qph) {
+        mbar_wait(&q_full[s], qph);
+        tc_fence_after();
+        issue_st(Cfg::ST_COL, k_k, desc_shift(q_k0, s * Cfg::Q_TILE), s_full);
+      };
+      auto issue_dp = [&](int it) {
+        mbar_wait(&do_full[it & 1], (it >> 1) & 1);
+        tc_fence_after();
+        issue_st(Cfg::DPT_COL + (it & 1) * 64, v_k, desc_shift(do_k0, (it & 1) * Cfg::Q_TILE), &dp_full[it & 1]);
+      };
+      mbar_wait(kv_full, 0);
+      int s_cur = 0;
+      uint32_t ph_cur = 0;
+      issue_s(0, 0, 0);
+      issue_dp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const uint32_t ph = it & 1;
+        const int s_nxt = (s_cur == 2) ? 0 : s_cur + 1;
+        const uint32_t ph_nxt = (s_nxt == 0) ? (ph_cur ^ 1) : ph_cur;
+        // dV += Pᵀ(it) · dO(it)          A: packed bf16 in the Sᵀ columns;  B: dO as MN-major [k = query][n = c]
+        mbar_wait(p_ready, ph);
+        tc_fence_after();
+        const uint64_t do_mn = desc_shift(do_mn0, (it & 1) * Cfg::Q_TILE), q_mn = desc_shift(q_mn0, s_cur * Cfg::Q_TILE);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16_ts(tmem + Cfg::DV_COL, tmem + Cfg::ST_COL + a_col(ks), desc_shift(do_mn, ks * 2048), idesc_ts, (it | ks) != 0);
+          umma_commit(&do_empty[it & 1]);
+        }
+        __syncwarp();
+        // next tile's Sᵀ (its columns: Pᵀ(it) was consumed by dV(it), just ahead in the pipe) and dPᵀ (other buffer: dSᵀ(it-1)
+        // was consumed by dK(it-1)) -- both are in TMEM before the softmax warps finish dS(it), so they never wait for them
+        if (it + 1 < n_it) {
+          issue_s(it + 1, s_nxt, ph_nxt);
+          issue_dp(it + 1);
+        }
+        // dK += dSᵀ(it) · Q(it) ;  dQᵀ(it) = Kᵀ · dS(it)
+        mbar_wait(ds_ready, ph);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16_ts(tmem + Cfg::DK_COL, tmem + Cfg::DPT_COL + (it & 1) * 64 + a_col(ks), desc_shift(q_mn, ks * 2048), idesc_ts, (it | ks) != 0);
+          umma_commit(&q_empty[s_cur]);
+        }
+        __syncwarp();
+        if (it > 0) {
+          mbar_wait(dq_drained, ph ^ 1);           // dQᵀ(it-1) read out of its columns by the drain warps
+          tc_fence_after();
+        }
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16_ss(tmem + Cfg::DQT_COL, desc_shift(k_mn, ks * 2048), desc_shift(ds_mn, ks * 2048), idesc_dq, ks != 0);
+          umma_commit(dq_full);
+        }
+        __syncwarp();
+        s_cur = s_nxt;
+        ph_cur = ph_nxt;
+      }
+    }
+  } else if (warp >= W_DRAIN) {
+    // ------------------------------- dQ drain warps -------------------------------
+    // dQᵀ(j): lane = head-dim index, 64 query columns  ->  transposed into fp32 staging rows of 32 head-dim values (one
+    // 128-byte swizzled row per query and 32-column box)  ->  TMA reduce-add into dq_accum.  Runs a tile behind the softmax
+    // warps and never blocks them: the only consumer of dq_drained is the MMA warp (before it overwrites the columns).
+    const int quarter = warp & 3;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const bool issuer = (warp == W_DRAIN && lane == 0);
+    const int l4 = lane >> 2;
+    for (int j = 0; j < n_it; ++j) {
+      mbar_wait(dq_full, j & 1);
+      tc_fence_after();
+      uint32_t dq0[32], dq1[32];
+      tmem_ld_x32(t_lane + Cfg::DQT_COL, dq0);
+      tmem_ld_x32(t_lane + Cfg::DQT_COL + 32, dq1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_drained);
+      uint8_t* stg = sStg + (j & 1) * Cfg::STG + quarter * (64 * 128) + (lane & 3) * 4;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        *reinterpret_cast<uint32_t*>(stg + e * 128 + ((l4 ^ (e & 7)) << 4)) = dq0[e];
+        *reinterpret_cast<uint32_t*>(stg + (32 + e) * 128 + ((l4 ^ (e & 7)) << 4)) = dq1[e];
+      }
+      fence_proxy_async_smem();
+      if (issuer) tma_wait_group_read<0>();        // reduce-add(j-1) has left the other buffer (tile j+1 stages there)
+      named_bar_sync(1, Cfg::NDT);
+      if (issuer) {
+        if (!(dbg & 1))                            // MIDGPT_ATTN_DEBUG=1: what-if without the reduce-add (wrong dQ)
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx) tma_reduce_add_3d(&tmdQ, sStg + (j & 1) * Cfg::STG + bx * (64 * 128), h * C + bx * 32, kv0 + j * 64, b);
+        tma_commit_group();
+      }
+    }
+    if (issuer) tma_wait_group<0>();
+  } else {
+    // ------------------------------- softmax warps -------------------------------
+    const int quarter = warp & 3, grp = warp >> 2;   // TMEM lane quarter, query-column group
+    const int row = quarter * 32 + lane;             // key row inside the tile == TMEM lane
+    const int kv_idx = kv0 + row;
+    const int c0 = grp * CPT;                        // this thread's first query column
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float sl2 = scale * kLog2e;
+
+    int s = 0;
+    uint32_t qph = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = it & 1;
+      const int q0 = kv0 + it * 64;
+      mbar_wait(&q_full[s], qph);                    // statistics of this tile are in shared memory
+      const float4* st_lse = reinterpret_cast<const float4*>(sStat + s * Cfg::STAT) + c0 / 4;
+      const float4* st_del = st_lse + 16;
+      float p[CPT];
+      // ---- Pᵀ = exp2(Sᵀ·c − lse·log2e)
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      {
+        uint32_t r[CPT];
+        tmem_ld_x32(t_lane + Cfg::ST_COL + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < CPT / 4; ++g) {
+          const float4 l4 = st_lse[g];
+          p[4 * g] = exp2f(fmaf(__uint_as_float(r[4 * g]), sl2, -l4.x));
+          p[4 * g + 1] = exp2f(fmaf(__uint_as_float(r[4 * g + 1]), sl2, -l4.y));
+          p[4 * g + 2] = exp2f(fmaf(__uint_as_float(r[4 * g + 2]), sl2, -l4.z));
+          p[4 * g + 3] = exp2f(fmaf(__uint_as_float(r[4 * g + 3]), sl2, -l4.w));
+        }
+        if (it < 2) {                                // the two 64-row tiles on the diagonal of this 128-key tile
+#pragma unroll
+          for (int e = 0; e < CPT; ++e)
+            if (kv_idx > q0 + c0 + e || kv_idx >= T) p[e] = 0.f;
+        }
+        uint32_t pk[CPT / 2];
+#pragma unroll
+        for (int e = 0; e < CPT / 2; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
+        tmem_st_x16(t_lane + Cfg::ST_COL + c0, pk);     // over this thread's own (already read) Sᵀ columns
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      // ---- dSᵀ = Pᵀ ∘ (dPᵀ·scale − δ·scale)
+      mbar_wait(&dp_full[it & 1], (it >> 1) & 1);
+      tc_fence_after();
+      {
+        uint32_t d[CPT];
+        tmem_ld_x32(t_lane + Cfg::DPT_COL + (it & 1) * 64 + c0, d);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < CPT / 4; ++g) {
+          const float4 d4 = st_del[g];
+          p[4 * g] *= fmaf(__uint_as_float(d[4 * g]), scale, -d4.x);
+          p[4 * g + 1] *= fmaf(__uint_as_float(d[4 * g + 1]), scale, -d4.y);
+          p[4 * g + 2] *= fmaf(__uint_as_float(d[4 * g + 2]), scale, -d4.z);
+          p[4 * g + 3] *= fmaf(__uint_as_float(d[4 * g + 3]), scale, -d4.w);
+        }
+        uint32_t pk[CPT / 2];
+#pragma unroll
+        for (int e = 0; e < CPT / 2; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
+        tmem_st_x16(t_lane + Cfg::DPT_COL + (it & 1) * 64 + c0, pk);
+        if (it > 0) mbar_wait(dq_full, ph ^ 1);    // dQᵀ(it-1) has retired: the (single) dSᵀ shared-memory tile may be overwritten
+        // the same values as the MN-major B tile of the dQᵀ product: row = key, 64 queries (128 bytes, swizzled) per row
+        uint8_t* rowp = sDS + row * 128;
+#pragma unroll
+        for (int g = 0; g < CPT / 8; ++g)
+          *reinterpret_cast<uint4*>(rowp + (((c0 / 8 + g) ^ (row & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(ds_ready);
+      if (++s == 3) { s = 0; qph ^= 1; }
+    }
+    // ---- epilogue: dV, dK (thread = key row x 64 columns) -> bf16 swizzled tiles in the (now idle) Q / dO stages -> TMA store,
+    //      which also clips key rows past T.  dq_full(last) covers every MMA of this CTA.
+    mbar_wait(dq_full, (n_it - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint8_t* tile = which ? sdO : sQ;
+      const uint32_t col = (which ? Cfg::DK_COL : Cfg::DV_COL) + grp * 64;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(t_lane + col + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v4;
+          v4.x = pack_bf16(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
+          v4.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+          v4.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+          v4.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+          st_swizzled_chunk(tile, 128, row, grp * 8 + ch * 4 + g, v4);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(2, Cfg::NST);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        tma_store_4d(&tmdV, sQ + cb * (128 * 128), cb * 64, h, kv0, b);
+        tma_store_4d(&tmdK, sdO + cb * (128 * 128), cb * 64, h, kv0, b);
+      }
+      tma_commit_group();
+      tma_wait_group<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc<512>(tmem);
+}
+
+// ================================================================================================
 // launchers
 // ================================================================================================
 template <typename K>
@@ -744,9 +1134,9 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
   const long long nvec = static_cast<long long>(B) * T * H;
   if (nvec >= (1ll << 31)) throw std::runtime_error("attention: too many (token, head) vectors for 32-bit indexing");
   if (C == 64)
-    attn_bwd_prep_kernel<64, 4><<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, static_cast<unsigned>(nvec), T, H);
+    attn_bwd_prep_kernel<64, 4><<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, lse, scale, static_cast<size_t>(B) * H * T, static_cast<unsigned>(nvec), T, H);
   else if (C == 128)
-    attn_bwd_prep_kernel<128, 4><<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, static_cast<unsigned>(nvec), T, H);
+    attn_bwd_prep_kernel<128, 4><<<num_sms * 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, lse, scale, static_cast<size_t>(B) * H * T, static_cast<unsigned>(nvec), T, H);
   else
     throw std::runtime_error("attention: head_dim must be 64 or 128");
   check("attn_bwd_prep");
@@ -755,7 +1145,16 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
               tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, 128), tdo = make_tmap_bthc(dout, B, T, H, C, static_cast<long long>(H) * C, 128);
   CUtensorMap tdq = make_tmap_dq(dq_accum, B, T, H * C);
   static const int dbg = [] { const char* e = getenv("MIDGPT_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
-  if (C == 64) {
+  static const bool use_v2 = [] { const char* e = getenv("MIDGPT_ATTN_BWD"); return e && std::string(e) == "v2"; }();
+  if (C == 128 && T % 64 == 0 && !use_v2) {
+    CUtensorMap tq64 = make_tmap_bthc(q, B, T, H, C, q_row_stride, 64), tdo64 = make_tmap_bthc(dout, B, T, H, C, static_cast<long long>(H) * C, 64);
+    CUtensorMap tdq64 = make_tmap_dq(dq_accum, B, T, H * C, 64);
+    const size_t plane = static_cast<size_t>(B) * H * T;          // delta planes: raw | delta*scale | lse*log2e (attn_bwd_prep_kernel)
+    CUtensorMap tdk = make_tmap_bthc(dk, B, T, H, C, dqkv_row_stride, 128), tdv = make_tmap_bthc(dv, B, T, H, C, dqkv_row_stride, 128);
+    static bool once = (set_smem(attn_bwd3_kernel, Bwd3Cfg::SMEM), true);
+    (void)once;
+    attn_bwd3_kernel<<<grid, Bwd3Cfg::THREADS, Bwd3Cfg::SMEM, s>>>(tq64, tk, tv, tdo64, tdq64, tdk, tdv, delta + 2 * plane, delta + plane, T, H, scale, dbg);
+  } else if (C == 64) {
     static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
     (void)once;
     attn_bwd_kernel<64><<<grid, BwdCfg<64>::THREADS, BwdCfg<64>::SMEM, s>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk),

@@ -287,7 +287,7 @@ at::Tensor attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& 
   const int64_t B = q.size(0), T = q.size(1), H = q.size(2), C = q.size(3);
   TORCH_CHECK(o.is_contiguous() && dout.is_contiguous());
   auto dqkv = at::empty({B * T, 3 * H * C}, q.options());
-  auto delta = at::empty({B, H, T}, lse.options());
+  auto delta = at::empty({3, B, H, T}, lse.options());   // delta | delta*scale | lse*log2(e)
   auto dq_accum = at::zeros({B * T, H * C}, lse.options());
   char* base = static_cast<char*>(dqkv.data_ptr());
   mg::attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(),

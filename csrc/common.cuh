@@ -256,6 +256,11 @@ MG_DEVICE void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+MG_DEVICE void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 MG_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -320,6 +325,12 @@ MG_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32
   d |= static_cast<uint64_t>(2) << 61;                               // layout type = SWIZZLE_128B
   return d;
 }
+
+// Descriptor of the same tile `byte_off` bytes further on.  The start-address field is the low 14 bits (address >> 4) and a
+// tile never wraps the shared-memory window, so this is ONE 64-bit add -- issue loops hoist make_smem_desc() out and shift
+// by compile-time offsets; rebuilding the descriptor per MMA made the single issuing thread the bottleneck of attention
+// (≈16 instructions per tcgen05.mma).
+MG_DEVICE uint64_t desc_shift(uint64_t d, uint32_t byte_off) { return d + static_cast<uint64_t>(byte_off >> 4); }
 
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, shape M x N, per-operand major-ness.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {

@@ -306,8 +306,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && (!CG2 || cta_rank == 0)) {           // CG2: only the leader CTA issues MMAs
+    // The whole warp runs the (converged) control flow so that descriptors and addresses live in uniform registers; one
+    // elected lane issues each k-block's tcgen05 instructions.  (With `if (lane == 0)` around the loop the compiler wraps
+    // every MMA in a register->uniform-register waterfall and rebuilds both descriptors: ~20 instructions per MMA.)
+    if (!CG2 || cta_rank == 0) {                          // CG2: only the leader CTA issues MMAs
       constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(CG2 ? 2 * BM : BM, BN) : make_idesc_bf16(CG2 ? 2 * BM : BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      const uint64_t a_desc0 = A_MN ? make_smem_desc(smem_u32(smem), BK * 128, 1024) : make_smem_desc(smem_u32(smem), 16, 1024);
+      const uint64_t b_desc0 = B_MN ? make_smem_desc(smem_u32(smem) + A_STAGE_BYTES, BK * 128, 1024)
+                                    : make_smem_desc(smem_u32(smem) + A_STAGE_BYTES, 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -322,26 +328,35 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * STG);
-          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          const uint64_t a_desc = desc_shift(a_desc0, stage * STG), b_desc = desc_shift(b_desc0, stage * STG);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc(a_base + k * 2048, BK * 128, 1024)
-                                     : make_smem_desc(a_base + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, BK * 128, 1024)
-                                     : make_smem_desc(b_base + k * 32, 16, 1024);
-            const uint32_t acc = ((kb - kb0) | k) != 0 ? 1u : 0u;
-            if (FP8 && CG2) umma_fp8_ss_cg2(d_tmem, da, db, idesc, acc);
-            else if (FP8) umma_fp8_ss(d_tmem, da, db, idesc, acc);
-            else if (CG2) umma_bf16_ss_cg2(d_tmem, da, db, idesc, acc);
-            else umma_bf16_ss(d_tmem, da, db, idesc, acc);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = desc_shift(a_desc, A_MN ? k * 2048 : k * 32);
+              const uint64_t db = desc_shift(b_desc, B_MN ? k * 2048 : k * 32);
+              const uint32_t acc = ((kb - kb0) | k) != 0 ? 1u : 0u;
+              if (FP8 && CG2) umma_fp8_ss_cg2(d_tmem, da, db, idesc, acc);
+              else if (FP8) umma_fp8_ss(d_tmem, da, db, idesc, acc);
+              else if (CG2) umma_bf16_ss_cg2(d_tmem, da, db, idesc, acc);
+              else umma_bf16_ss(d_tmem, da, db, idesc, acc);
+            }
+            if (CG2) umma_commit_mc2(&empty_bar[stage]);   // frees the smem slot in BOTH CTAs when these MMAs retire
+            else umma_commit(&empty_bar[stage]);
+            if (kb + 1 == kb1) {
+              if (CG2) umma_commit_mc2(&tfull_bar[buf]);   // accumulator complete -> both CTAs' epilogues
+              else umma_commit(&tfull_bar[buf]);
+            }
           }
-          if (CG2) umma_commit_mc2(&empty_bar[stage]);   // frees the smem slot in BOTH CTAs when these MMAs retire
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        if (CG2) umma_commit_mc2(&tfull_bar[buf]);       // accumulator complete -> both CTAs' epilogues
-        else umma_commit(&tfull_bar[buf]);
+        if (kb0 >= kb1) {                                  // empty K slice (never produced by pick_split_k): still hand the buffer on
+          if (elect_one()) {
+            if (CG2) umma_commit_mc2(&tfull_bar[buf]);
+            else umma_commit(&tfull_bar[buf]);
+          }
+          __syncwarp();
+        }
       }
     }
   } else {

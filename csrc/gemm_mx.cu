@@ -135,8 +135,11 @@ gemm_mxfp8_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp converged (descriptors stay in uniform registers), one elected lane issues each stage's tcgen05 instructions
+    {
       constexpr uint32_t idesc0 = idesc_mxf8(BM, BN);
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), 16, 1024), b_desc0 = make_smem_desc(smem_u32(smem) + A_BYTES, 16, 1024);
+      const uint64_t sf_desc0 = desc_noswz(smem_u32(sSF), 16, 128);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -146,24 +149,24 @@ gemm_mxfp8_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * AB_BYTES);
-          const uint32_t b_base = a_base + A_BYTES;
-          const uint32_t sf_base = smem_u32(sSF + stage * SF_BYTES);
-          // scale factors smem -> TMEM (tcgen05.cp and tcgen05.mma execute in issue order: no hazard with the previous stage)
-          tc_cp_32x128b_warpx4(tmem + SFA_COL, desc_noswz(sf_base, 16, 128));
-          tc_cp_32x128b_warpx4(tmem + SFB_COL, desc_noswz(sf_base + 512, 16, 128));
-          tc_cp_32x128b_warpx4(tmem + SFB_COL + 4, desc_noswz(sf_base + 1024, 16, 128));
+          const uint64_t a_desc = desc_shift(a_desc0, stage * AB_BYTES), b_desc = desc_shift(b_desc0, stage * AB_BYTES);
+          const uint64_t sf_desc = desc_shift(sf_desc0, stage * SF_BYTES);
+          if (elect_one()) {
+            // scale factors smem -> TMEM (tcgen05.cp and tcgen05.mma execute in issue order: no hazard with the previous stage)
+            tc_cp_32x128b_warpx4(tmem + SFA_COL, sf_desc);
+            tc_cp_32x128b_warpx4(tmem + SFB_COL, desc_shift(sf_desc, 512));
+            tc_cp_32x128b_warpx4(tmem + SFB_COL + 4, desc_shift(sf_desc, 1024));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {                       // 4 x K=32 per stage; sf_id = k selects the k-block's scale byte
-            const uint64_t da = make_smem_desc(a_base + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(b_base + k * 32, 16, 1024);
-            const uint32_t idesc = idesc0 | (static_cast<uint32_t>(k) << 4) | (static_cast<uint32_t>(k) << 29);
-            umma_mxf8_ss(tmem + D_COL, da, db, idesc, tmem + SFA_COL, tmem + SFB_COL, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {                     // 4 x K=32 per stage; sf_id = k selects the k-block's scale byte
+              const uint32_t idesc = idesc0 | (static_cast<uint32_t>(k) << 4) | (static_cast<uint32_t>(k) << 29);
+              umma_mxf8_ss(tmem + D_COL, desc_shift(a_desc, k * 32), desc_shift(b_desc, k * 32), idesc, tmem + SFA_COL, tmem + SFB_COL, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb + 1 == num_k) umma_commit(tfull_bar);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar);
       }
     }
   } else {

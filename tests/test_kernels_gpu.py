@@ -153,7 +153,7 @@ def test_dropout_statistics(be):
 
 
 # ----------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("B,T,H,C", [(2, 256, 3, 64), (1, 512, 2, 128), (2, 200, 2, 64), (1, 1024, 2, 128)])
+@pytest.mark.parametrize("B,T,H,C", [(2, 256, 3, 64), (1, 512, 2, 128), (2, 200, 2, 64), (1, 1024, 2, 128), (2, 192, 2, 128), (1, 200, 2, 128)])
 def test_flash_attention_fwd_bwd(be, ref, B, T, H, C):
     torch.manual_seed(8)
     D = H * C
