@@ -783,7 +783,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sStg = sDS + Cfg::DS;                         // 2 buffers
   uint8_t* sStat = sStg + 2 * Cfg::STG;                  // NQ x (lse2[64] | dsc[64])
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + Cfg::NQ * Cfg::STAT);
-  uint64_t* kv_full = bars;
+  uint64_t* k_full = bars;
   uint64_t* q_full = bars + 1;       // [3] Q tile + its statistics landed
   uint64_t* q_empty = bars + 4;      // [3] dK(i) retired: Q stage (and its statistics) reusable
   uint64_t* do_full = bars + 7;      // [2]
@@ -794,7 +794,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* ds_ready = bars + 15;    // NST arrivals: dSᵀ(i) in TMEM and in shared memory
   uint64_t* dq_full = bars + 16;     // dQᵀ(i) (and everything issued before it) retired
   uint64_t* dq_drained = bars + 17;  // NDT arrivals: dQᵀ(i) read out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* v_full = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x;
@@ -805,7 +806,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
     tma_prefetch_desc(&tmdK); tma_prefetch_desc(&tmdV);
-    mbar_init(kv_full, 1);
+    mbar_init(k_full, 1); mbar_init(v_full, 1);
     for (int s = 0; s < 3; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&do_full[s], 1); mbar_init(&do_empty[s], 1); mbar_init(&dp_full[s], 1); }
     mbar_init(s_full, 1);
@@ -822,12 +823,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == W_TMA) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * Cfg::KV_TILE);
-#pragma unroll
-      for (int cb = 0; cb < C / 64; ++cb) {
-        tma_load_4d(sK + cb * (128 * 128), &tmK, kv_full, cb * 64, h, kv0, b);
-        tma_load_4d(sV + cb * (128 * 128), &tmV, kv_full, cb * 64, h, kv0, b);
-      }
+      // issue order = order of first use: Q(0) and K feed Sᵀ(0); dO(0) and V feed dPᵀ(0)
       int s = 0;
       uint32_t qph = 0;
       for (int it = 0; it < n_it; ++it) {
@@ -838,11 +834,21 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sQ + s * Cfg::Q_TILE + cb * (64 * 128), &tmQ, &q_full[s], cb * 64, h, q0, b);
         bulk_load_1d(sStat + s * Cfg::STAT, lse2 + stat_row + q0, 256, &q_full[s]);
         bulk_load_1d(sStat + s * Cfg::STAT + 256, dsc + stat_row + q0, 256, &q_full[s]);
+        if (it == 0) {
+          mbar_expect_tx(k_full, Cfg::KV_TILE);
+#pragma unroll
+          for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sK + cb * (128 * 128), &tmK, k_full, cb * 64, h, kv0, b);
+        }
         const int d = it & 1;
         mbar_wait(&do_empty[d], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&do_full[d], Cfg::Q_TILE);
 #pragma unroll
         for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sdO + d * Cfg::Q_TILE + cb * (64 * 128), &tmdO, &do_full[d], cb * 64, h, q0, b);
+        if (it == 0) {
+          mbar_expect_tx(v_full, Cfg::KV_TILE);
+#pragma unroll
+          for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sV + cb * (128 * 128), &tmV, v_full, cb * 64, h, kv0, b);
+        }
         if (++s == 3) { s = 0; qph ^= 1; }
       }
     }
@@ -884,10 +890,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         issue_st(Cfg::DPT_COL + (it & 1) * 64, v_k, desc_shift(do_k0, (it & 1) * Cfg::Q_TILE), &dp_full[it & 1]);
       };
-      mbar_wait(kv_full, 0);
       int s_cur = 0;
       uint32_t ph_cur = 0;
+      mbar_wait(k_full, 0);
       issue_s(0, 0, 0);
+      mbar_wait(v_full, 0);
       issue_dp(0);
       for (int it = 0; it < n_it; ++it) {
         const uint32_t ph = it & 1;
