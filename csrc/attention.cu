@@ -16,6 +16,7 @@
 //   vector atomics.  Every operand tile is loaded once and used through both K-major and MN-major descriptors.
 #include "common.cuh"
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 
@@ -730,22 +731,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ================================================================================================
-// Backward, version 3 (head_dim 128, T % 64 == 0): transposed scores, P/dS kept in tensor memory, 64-row query tiles.
+// Backward, version 3 (head_dim 128, T % 64 == 0): transposed scores, P/dS kept in tensor memory, 64-row query tiles,
+// persistent CTAs.
 //
-//   One CTA = one (batch, head, 128-key tile); loop over 64-row query tiles at or below the diagonal.
+//   Work item = one (batch, head, 128-key tile); inside it a loop over the 64-row query tiles at or below the diagonal.
 //   Sᵀ = K·Qᵀ and dPᵀ = V·dOᵀ put KEYS on the TMEM lanes, so Pᵀ and dSᵀ (bf16, packed two per column, written back over
 //   the fp32 columns they came from with tcgen05.st) are directly the A operands of dV += Pᵀ·dO and dK += dSᵀ·Q
 //   (tcgen05.mma with A in TMEM): no P tile in shared memory, half the operand traffic for those two products.
 //   dQᵀ = Kᵀ·dS (M = head_dim, N = 64 queries) has its OWN 64 TMEM columns and dPᵀ is double buffered, so nothing in a tile
 //   aliases the next one.  Tensor-pipe order:  dV(i) | S(i+1) dP(i+1) | dK(i) dQ(i): the next tile's scores and dP are in
-//   TMEM before the softmax warps finish dS(i), so their loop P(i) → dS(i) → P(i+1) never waits for the tensor core, and
-//   the dQ(i) drain (transposing staging store + TMA reduce-add, double buffered) runs on four dedicated warps one tile
-//   behind.  Version 2 (above in the file, still used for head_dim 64 / ragged T) had to walk each tile in lock step
-//   because dQ aliased dP and P, dS and the dQ staging shared one buffer.
+//   TMEM before the softmax warps finish dS(i), so their loop P(i) → dS(i) → P(i+1) never waits for the tensor core.
+//   Four dedicated warps move results out one tile behind: dQ(i) (transposing staging store + TMA reduce-add) and, at the
+//   end of an item, dV/dK (bf16 tiles + TMA store).
+//   One CTA per SM walks a static list of items (heaviest key tiles first, round-robin over CTAs); every pipeline runs
+//   on a tile counter that keeps counting across items, so the K/V/Q loads and the first Sᵀ/dPᵀ of the next item overlap
+//   the dQ drain and the dV/dK epilogue of the current one -- with one CTA per item ~30 % of the kernel at T = 1024 was
+//   pipeline fill and drain.  Version 2 (above in the file, still used for head_dim 64 / ragged T) had to walk each tile
+//   in lock step because dQ aliased dP and P, dS and the dQ staging shared one buffer.
 //
 //   TMEM columns:  Sᵀ 0..63 (Pᵀ packed in the first 16 columns of each 32-column half) | dPᵀ[2] 64..191 (dSᵀ packed
 //   likewise) | dQᵀ 192..255 | dV 256..383 | dK 384..511
-//   warps 0-7 softmax (thread = key row × 32-query half), 8-11 dQ drain, 12 TMA producer, 13 MMA issuer.
+//   warps 0-7 softmax (thread = key row × 32-query half), 8-11 output (dQ drain, dV/dK), 12 TMA producer, 13 MMA issuer.
 // ================================================================================================
 struct Bwd3Cfg {
   static constexpr int C = 128, BQ = 64;
@@ -753,11 +759,11 @@ struct Bwd3Cfg {
   static constexpr int Q_TILE = BQ * C * 2;            // Q or dO  [64 x C] bf16
   static constexpr int NQ = 3, NDO = 2;                // pipeline depth of the Q and dO stages
   static constexpr int DS = 128 * BQ * 2;              // dSᵀ [128 keys x 64 queries] bf16 (B operand of the dQᵀ product)
-  static constexpr int STG = BQ * C * 4;               // dQ staging [64 queries x C] fp32, 2 buffers
+  static constexpr int STG = BQ * C * 4;               // dQ staging [64 queries x C] fp32, 2 buffers; they double as the dV / dK output tiles
   static constexpr int STAT = 2 * BQ * 4;              // lse·log2e | delta·scale of one query tile
-  static constexpr int SMEM = 2 * KV_TILE + (NQ + NDO) * Q_TILE + DS + 2 * STG + NQ * STAT + 256;
+  static constexpr int SMEM = 2 * KV_TILE + (NQ + NDO) * Q_TILE + DS + 2 * STG + NQ * STAT + 512;   // + barriers, item ring
   static constexpr int ST_COL = 0, DPT_COL = 64, DQT_COL = 192, DV_COL = 256, DK_COL = 384;   // dPᵀ: 2 buffers of 64 columns
-  static constexpr int NSW = 8, NDW = 4;               // softmax warps (P, dS, final dV/dK epilogue), dQ drain warps
+  static constexpr int NSW = 8, NDW = 4;               // softmax warps (P, dS), output warps (dQ drain, dV/dK epilogue)
   static constexpr int NST = 32 * NSW, NDT = 32 * NDW;
   static constexpr int THREADS = NST + NDT + 64;       // + TMA warp + MMA warp
   static constexpr int CPT = 64 * 4 / NSW;             // query columns per softmax thread: 4 lane quarters x 2 column groups
@@ -768,22 +774,22 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                  const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
                  const __grid_constant__ CUtensorMap tmdV, const float* __restrict__ lse2, const float* __restrict__ dsc,
-                 int T, int H, float scale, int dbg) {
+                 int T, int H, int n_items, int* __restrict__ sched, float scale, int dbg) {
   using Cfg = Bwd3Cfg;
   constexpr int C = Cfg::C, CPT = Cfg::CPT;
-  constexpr int W_DRAIN = Cfg::NSW, W_TMA = Cfg::NSW + Cfg::NDW, W_MMA = W_TMA + 1;
+  constexpr int W_OUT = Cfg::NSW, W_TMA = Cfg::NSW + Cfg::NDW, W_MMA = W_TMA + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sK = smem;
   uint8_t* sV = sK + Cfg::KV_TILE;
-  uint8_t* sQ = sV + Cfg::KV_TILE;                       // NQ stages; reused as the dV output tile at the end
-  uint8_t* sdO = sQ + Cfg::NQ * Cfg::Q_TILE;             // NDO stages; reused as the dK output tile at the end
+  uint8_t* sQ = sV + Cfg::KV_TILE;                       // NQ stages
+  uint8_t* sdO = sQ + Cfg::NQ * Cfg::Q_TILE;             // NDO stages
   uint8_t* sDS = sdO + Cfg::NDO * Cfg::Q_TILE;
   uint8_t* sStg = sDS + Cfg::DS;                         // 2 buffers
   uint8_t* sStat = sStg + 2 * Cfg::STG;                  // NQ x (lse2[64] | dsc[64])
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + Cfg::NQ * Cfg::STAT);
-  uint64_t* k_full = bars;
+  uint64_t* k_full = bars;           // per item
   uint64_t* q_full = bars + 1;       // [3] Q tile + its statistics landed
   uint64_t* q_empty = bars + 4;      // [3] dK(i) retired: Q stage (and its statistics) reusable
   uint64_t* do_full = bars + 7;      // [2]
@@ -794,19 +800,36 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* ds_ready = bars + 15;    // NST arrivals: dSᵀ(i) in TMEM and in shared memory
   uint64_t* dq_full = bars + 16;     // dQᵀ(i) (and everything issued before it) retired
   uint64_t* dq_drained = bars + 17;  // NDT arrivals: dQᵀ(i) read out of TMEM
-  uint64_t* v_full = bars + 18;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* v_full = bars + 18;      // per item
+  uint64_t* kv_free = bars + 19;     // per item: every MMA that reads this item's K / V has retired
+  uint64_t* acc_free = bars + 20;    // per item, NDT arrivals: dV / dK accumulators read out of TMEM
+  uint64_t* item_full = bars + 21;   // [8] work-item ring: slot i holds the id of this CTA's (8k+i)-th item (-1 = no more work)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  volatile int* item_q = reinterpret_cast<volatile int*>(bars + 30);   // [8]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int kv0 = jt * 128;
-  const int n_it = T / 64 - 2 * jt;                // query tiles kv0/64 .. T/64-1
+  const int nq64 = T / 64;
+  // Work items are handed out dynamically (one global counter, fetched by the TMA producer and passed to the other roles
+  // through an 8-slot shared-memory ring: no role can be more than a few tiles -- at most three items -- behind it).
+  // item w -> (batch*head, key tile): the key tiles of one (batch, head) are consecutive and start with the longest loop, so
+  // the CTAs running at any moment share that head's Q / dO / dq_accum in L2, exactly like a plain grid would.
+  const int njt = (T + 127) / 128;
+  auto decode = [&](int w, int& jt, int& h, int& b) {
+    const int bh = w / njt;
+    jt = w - bh * njt;
+    b = bh / H;
+    h = bh - b * H;
+  };
+  auto next_item = [&](int ic) {                     // consumer side of the ring
+    mbar_wait(&item_full[ic & 7], (ic >> 3) & 1);
+    return item_q[ic & 7];
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
     tma_prefetch_desc(&tmdK); tma_prefetch_desc(&tmdV);
-    mbar_init(k_full, 1); mbar_init(v_full, 1);
+    mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(kv_free, 1); mbar_init(acc_free, Cfg::NDT);
+    for (int i = 0; i < 8; ++i) mbar_init(&item_full[i], 1);
     for (int s = 0; s < 3; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&do_full[s], 1); mbar_init(&do_empty[s], 1); mbar_init(&dp_full[s], 1); }
     mbar_init(s_full, 1);
@@ -818,38 +841,55 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const long long stat_row = (static_cast<long long>(b) * H + h) * T;
 
   if (warp == W_TMA) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
-      // issue order = order of first use: Q(0) and K feed Sᵀ(0); dO(0) and V feed dPᵀ(0)
-      int s = 0;
+      int s = 0, g = 0;
       uint32_t qph = 0;
-      for (int it = 0; it < n_it; ++it) {
-        const int q0 = kv0 + it * 64;
-        mbar_wait(&q_empty[s], qph ^ 1);
-        mbar_expect_tx(&q_full[s], Cfg::Q_TILE + Cfg::STAT);
+      for (int ic = 0;; ++ic) {
+        int w = atomicAdd(sched, 1);
+        if (w >= n_items) w = -1;
+        item_q[ic & 7] = w;
+        mbar_arrive(&item_full[ic & 7]);              // release: the id is visible to whoever completes the wait
+        if (w < 0) break;
+        int jt, h, b;
+        decode(w, jt, h, b);
+        const int kv0 = jt * 128, n_it = nq64 - 2 * jt;
+        const long long stat_row = (static_cast<long long>(b) * H + h) * T;
+        // issue order = order of first use: Q(0) and K feed Sᵀ(0); dO(0) and V feed dPᵀ(0)
+        for (int it = 0; it < n_it; ++it, ++g) {
+          const int q0 = kv0 + it * 64;
+          mbar_wait(&q_empty[s], qph ^ 1);
+          mbar_expect_tx(&q_full[s], Cfg::Q_TILE + Cfg::STAT);
 #pragma unroll
-        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sQ + s * Cfg::Q_TILE + cb * (64 * 128), &tmQ, &q_full[s], cb * 64, h, q0, b);
-        bulk_load_1d(sStat + s * Cfg::STAT, lse2 + stat_row + q0, 256, &q_full[s]);
-        bulk_load_1d(sStat + s * Cfg::STAT + 256, dsc + stat_row + q0, 256, &q_full[s]);
-        if (it == 0) {
-          mbar_expect_tx(k_full, Cfg::KV_TILE);
+          for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sQ + s * Cfg::Q_TILE + cb * (64 * 128), &tmQ, &q_full[s], cb * 64, h, q0, b);
+          bulk_load_1d(sStat + s * Cfg::STAT, lse2 + stat_row + q0, 256, &q_full[s]);
+          bulk_load_1d(sStat + s * Cfg::STAT + 256, dsc + stat_row + q0, 256, &q_full[s]);
+          if (it == 0) {
+            mbar_wait(kv_free, (ic & 1) ^ 1);          // previous item's last MMA has retired
+            mbar_expect_tx(k_full, Cfg::KV_TILE);
 #pragma unroll
-          for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sK + cb * (128 * 128), &tmK, k_full, cb * 64, h, kv0, b);
+            for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sK + cb * (128 * 128), &tmK, k_full, cb * 64, h, kv0, b);
+          }
+          const int d = g & 1;
+          mbar_wait(&do_empty[d], ((g >> 1) & 1) ^ 1);
+          mbar_expect_tx(&do_full[d], Cfg::Q_TILE);
+#pragma unroll
+          for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sdO + d * Cfg::Q_TILE + cb * (64 * 128), &tmdO, &do_full[d], cb * 64, h, q0, b);
+          if (it == 0) {
+            mbar_expect_tx(v_full, Cfg::KV_TILE);
+#pragma unroll
+            for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sV + cb * (128 * 128), &tmV, v_full, cb * 64, h, kv0, b);
+          }
+          if (++s == 3) { s = 0; qph ^= 1; }
         }
-        const int d = it & 1;
-        mbar_wait(&do_empty[d], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&do_full[d], Cfg::Q_TILE);
-#pragma unroll
-        for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sdO + d * Cfg::Q_TILE + cb * (64 * 128), &tmdO, &do_full[d], cb * 64, h, q0, b);
-        if (it == 0) {
-          mbar_expect_tx(v_full, Cfg::KV_TILE);
-#pragma unroll
-          for (int cb = 0; cb < C / 64; ++cb) tma_load_4d(sV + cb * (128 * 128), &tmV, v_full, cb * 64, h, kv0, b);
-        }
-        if (++s == 3) { s = 0; qph ^= 1; }
+      }
+      // the last CTA to run out of work re-arms the counters for the next launch (they start at zero)
+      if (atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+        sched[1] = 0;
+        __threadfence();
+        sched[0] = 0;
       }
     }
   } else if (warp == W_MMA) {
@@ -880,99 +920,175 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         __syncwarp();
       };
-      auto issue_s = [&](int it, int s, uint32_t qph) {
+      auto issue_s = [&](int s, uint32_t qph) {                 // Sᵀ of the tile whose Q sits in stage s
         mbar_wait(&q_full[s], qph);
         tc_fence_after();
         issue_st(Cfg::ST_COL, k_k, desc_shift(q_k0, s * Cfg::Q_TILE), s_full);
       };
-      auto issue_dp = [&](int it) {
-        mbar_wait(&do_full[it & 1], (it >> 1) & 1);
+      auto issue_dp = [&](int g) {                               // dPᵀ of global tile g
+        mbar_wait(&do_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        issue_st(Cfg::DPT_COL + (it & 1) * 64, v_k, desc_shift(do_k0, (it & 1) * Cfg::Q_TILE), &dp_full[it & 1]);
+        issue_st(Cfg::DPT_COL + (g & 1) * 64, v_k, desc_shift(do_k0, (g & 1) * Cfg::Q_TILE), &dp_full[g & 1]);
       };
-      int s_cur = 0;
+      int s_cur = 0, g = 0;
       uint32_t ph_cur = 0;
-      mbar_wait(k_full, 0);
-      issue_s(0, 0, 0);
-      mbar_wait(v_full, 0);
-      issue_dp(0);
-      for (int it = 0; it < n_it; ++it) {
-        const uint32_t ph = it & 1;
-        const int s_nxt = (s_cur == 2) ? 0 : s_cur + 1;
-        const uint32_t ph_nxt = (s_nxt == 0) ? (ph_cur ^ 1) : ph_cur;
-        // dV += Pᵀ(it) · dO(it)          A: packed bf16 in the Sᵀ columns;  B: dO as MN-major [k = query][n = c]
-        mbar_wait(p_ready, ph);
-        tc_fence_after();
-        const uint64_t do_mn = desc_shift(do_mn0, (it & 1) * Cfg::Q_TILE), q_mn = desc_shift(q_mn0, s_cur * Cfg::Q_TILE);
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16_ts(tmem + Cfg::DV_COL, tmem + Cfg::ST_COL + a_col(ks), desc_shift(do_mn, ks * 2048), idesc_ts, (it | ks) != 0);
-          umma_commit(&do_empty[it & 1]);
-        }
-        __syncwarp();
-        // next tile's Sᵀ (its columns: Pᵀ(it) was consumed by dV(it), just ahead in the pipe) and dPᵀ (other buffer: dSᵀ(it-1)
-        // was consumed by dK(it-1)) -- both are in TMEM before the softmax warps finish dS(it), so they never wait for them
-        if (it + 1 < n_it) {
-          issue_s(it + 1, s_nxt, ph_nxt);
-          issue_dp(it + 1);
-        }
-        // dK += dSᵀ(it) · Q(it) ;  dQᵀ(it) = Kᵀ · dS(it)
-        mbar_wait(ds_ready, ph);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16_ts(tmem + Cfg::DK_COL, tmem + Cfg::DPT_COL + (it & 1) * 64 + a_col(ks), desc_shift(q_mn, ks * 2048), idesc_ts, (it | ks) != 0);
-          umma_commit(&q_empty[s_cur]);
-        }
-        __syncwarp();
-        if (it > 0) {
-          mbar_wait(dq_drained, ph ^ 1);           // dQᵀ(it-1) read out of its columns by the drain warps
+      for (int ic = 0;; ++ic) {
+        const int w = next_item(ic);
+        if (w < 0) break;
+        int jt, h_, b_;
+        decode(w, jt, h_, b_);
+        const int n_it = nq64 - 2 * jt;
+        mbar_wait(k_full, ic & 1);
+        issue_s(s_cur, ph_cur);
+        mbar_wait(v_full, ic & 1);
+        issue_dp(g);
+        for (int it = 0; it < n_it; ++it, ++g) {
+          const uint32_t ph = g & 1;
+          const int s_nxt = (s_cur == 2) ? 0 : s_cur + 1;
+          const uint32_t ph_nxt = (s_nxt == 0) ? (ph_cur ^ 1) : ph_cur;
+          // dV += Pᵀ(g) · dO(g)          A: packed bf16 in the Sᵀ columns;  B: dO as MN-major [k = query][n = c]
+          mbar_wait(p_ready, ph);
           tc_fence_after();
-        }
-        if (elect_one()) {
+          if (it == 0 && ic > 0) {
+            mbar_wait(acc_free, (ic - 1) & 1);       // the output warps have read the previous item's dV / dK out of TMEM
+            tc_fence_after();
+          }
+          const uint64_t do_mn = desc_shift(do_mn0, (g & 1) * Cfg::Q_TILE), q_mn = desc_shift(q_mn0, s_cur * Cfg::Q_TILE);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_bf16_ss(tmem + Cfg::DQT_COL, desc_shift(k_mn, ks * 2048), desc_shift(ds_mn, ks * 2048), idesc_dq, ks != 0);
-          umma_commit(dq_full);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_ts(tmem + Cfg::DV_COL, tmem + Cfg::ST_COL + a_col(ks), desc_shift(do_mn, ks * 2048), idesc_ts, (it | ks) != 0);
+            umma_commit(&do_empty[g & 1]);
+          }
+          __syncwarp();
+          // next tile's Sᵀ (its columns: Pᵀ(g) was consumed by dV(g), just ahead in the pipe) and dPᵀ (other buffer: dSᵀ(g-1)
+          // was consumed by dK(g-1)) -- both are in TMEM before the softmax warps finish dS(g), so they never wait for them
+          if (it + 1 < n_it) {
+            issue_s(s_nxt, ph_nxt);
+            issue_dp(g + 1);
+          }
+          // dK += dSᵀ(g) · Q(g) ;  dQᵀ(g) = Kᵀ · dS(g)
+          mbar_wait(ds_ready, ph);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_ts(tmem + Cfg::DK_COL, tmem + Cfg::DPT_COL + (g & 1) * 64 + a_col(ks), desc_shift(q_mn, ks * 2048), idesc_ts, (it | ks) != 0);
+            umma_commit(&q_empty[s_cur]);
+          }
+          __syncwarp();
+          if (g > 0) {
+            mbar_wait(dq_drained, ph ^ 1);           // dQᵀ(g-1) read out of its columns by the output warps
+            tc_fence_after();
+          }
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16_ss(tmem + Cfg::DQT_COL, desc_shift(k_mn, ks * 2048), desc_shift(ds_mn, ks * 2048), idesc_dq, ks != 0);
+            umma_commit(dq_full);
+            if (it + 1 == n_it) umma_commit(kv_free);
+          }
+          __syncwarp();
+          s_cur = s_nxt;
+          ph_cur = ph_nxt;
         }
-        __syncwarp();
-        s_cur = s_nxt;
-        ph_cur = ph_nxt;
       }
     }
-  } else if (warp >= W_DRAIN) {
-    // ------------------------------- dQ drain warps -------------------------------
-    // dQᵀ(j): lane = head-dim index, 64 query columns  ->  transposed into fp32 staging rows of 32 head-dim values (one
+  } else if (warp >= W_OUT) {
+    // ------------------------------- output warps -------------------------------
+    // dQᵀ(g): lane = head-dim index, 64 query columns  ->  transposed into fp32 staging rows of 32 head-dim values (one
     // 128-byte swizzled row per query and 32-column box)  ->  TMA reduce-add into dq_accum.  Runs a tile behind the softmax
     // warps and never blocks them: the only consumer of dq_drained is the MMA warp (before it overwrites the columns).
+    // After an item's last tile: dV and dK (lane = key row) -> bf16 swizzled tiles -> TMA store (clips key rows past T).
     const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const bool issuer = (warp == W_DRAIN && lane == 0);
+    const bool issuer = (warp == W_OUT && lane == 0);
     const int l4 = lane >> 2;
-    for (int j = 0; j < n_it; ++j) {
-      mbar_wait(dq_full, j & 1);
-      tc_fence_after();
-      uint32_t dq0[32], dq1[32];
-      tmem_ld_x32(t_lane + Cfg::DQT_COL, dq0);
-      tmem_ld_x32(t_lane + Cfg::DQT_COL + 32, dq1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(dq_drained);
-      uint8_t* stg = sStg + (j & 1) * Cfg::STG + quarter * (64 * 128) + (lane & 3) * 4;
+    int g = 0;
+    for (int ic = 0;; ++ic) {
+      const int w = next_item(ic);
+      if (w < 0) break;
+      int jt, h, b;
+      decode(w, jt, h, b);
+      const int kv0 = jt * 128, n_it = nq64 - 2 * jt;
+      for (int j = 0; j < n_it; ++j, ++g) {
+        mbar_wait(dq_full, g & 1);
+        tc_fence_after();
+        uint32_t dq0[32], dq1[32];
+        tmem_ld_x32(t_lane + Cfg::DQT_COL, dq0);
+        tmem_ld_x32(t_lane + Cfg::DQT_COL + 32, dq1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_drained);
+        if (issuer) {                              // staging buffer g & 1: its previous user is two bulk groups back
+          if (j == 0) tma_wait_group_read<0>();    // (first tile of an item: the previous item's dV / dK stores used both buffers)
+          else tma_wait_group_read<1>();
+        }
+        named_bar_sync(1, Cfg::NDT);
+        uint8_t* stg = sStg + (g & 1) * Cfg::STG + quarter * (64 * 128) + (lane & 3) * 4;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        *reinterpret_cast<uint32_t*>(stg + e * 128 + ((l4 ^ (e & 7)) << 4)) = dq0[e];
-        *reinterpret_cast<uint32_t*>(stg + (32 + e) * 128 + ((l4 ^ (e & 7)) << 4)) = dq1[e];
+        for (int e = 0; e < 32; ++e) {
+          *reinterpret_cast<uint32_t*>(stg + e * 128 + ((l4 ^ (e & 7)) << 4)) = dq0[e];
+          *reinterpret_cast<uint32_t*>(stg + (32 + e) * 128 + ((l4 ^ (e & 7)) << 4)) = dq1[e];
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, Cfg::NDT);
+        if (issuer) {
+          if (!(dbg & 1))                          // MIDGPT_ATTN_DEBUG=1: what-if without the reduce-add (wrong dQ)
+#pragma unroll
+          for (int bx = 0; bx < 4; ++bx) tma_reduce_add_3d(&tmdQ, sStg + (g & 1) * Cfg::STG + bx * (64 * 128), h * C + bx * 32, kv0 + j * 64, b);
+          tma_commit_group();
+        }
       }
+      // ---- item epilogue.  dq_full of the last tile (observed above) covers every MMA of the item.  dV goes out through the
+      //      staging buffer of the second-to-last tile, dK is packed in registers (so the accumulators are released before
+      //      waiting for the last reduce-add) and then goes out through the other buffer.
+      uint8_t* tile_v = sStg + (g & 1) * Cfg::STG;          // g already counts the next tile: (g & 1) == buffer of tile g-2
+      uint8_t* tile_k = sStg + ((g & 1) ^ 1) * Cfg::STG;
+      if (issuer) tma_wait_group_read<1>();
+      named_bar_sync(1, Cfg::NDT);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(t_lane + Cfg::DV_COL + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          st_swizzled_chunk(tile_v, 128, row, ch * 4 + q4,
+                            make_uint4(pack_bf16(__uint_as_float(r[8 * q4]), __uint_as_float(r[8 * q4 + 1])),
+                                       pack_bf16(__uint_as_float(r[8 * q4 + 2]), __uint_as_float(r[8 * q4 + 3])),
+                                       pack_bf16(__uint_as_float(r[8 * q4 + 4]), __uint_as_float(r[8 * q4 + 5])),
+                                       pack_bf16(__uint_as_float(r[8 * q4 + 6]), __uint_as_float(r[8 * q4 + 7]))));
+      }
+      uint32_t kk[64];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(t_lane + Cfg::DK_COL + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) kk[ch * 16 + e] = pack_bf16(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+      }
+      tc_fence_before();
+      mbar_arrive(acc_free);                       // the next item's first dV / dK MMAs may overwrite the accumulators
       fence_proxy_async_smem();
-      if (issuer) tma_wait_group_read<0>();        // reduce-add(j-1) has left the other buffer (tile j+1 stages there)
       named_bar_sync(1, Cfg::NDT);
       if (issuer) {
-        if (!(dbg & 1))                            // MIDGPT_ATTN_DEBUG=1: what-if without the reduce-add (wrong dQ)
 #pragma unroll
-        for (int bx = 0; bx < 4; ++bx) tma_reduce_add_3d(&tmdQ, sStg + (j & 1) * Cfg::STG + bx * (64 * 128), h * C + bx * 32, kv0 + j * 64, b);
+        for (int cb = 0; cb < 2; ++cb) tma_store_4d(&tmdV, tile_v + cb * (128 * 128), cb * 64, h, kv0, b);
+        tma_commit_group();
+        tma_wait_group_read<1>();                  // everything but the dV store: the last reduce-add has left tile_k
+      }
+      named_bar_sync(1, Cfg::NDT);
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc)
+        st_swizzled_chunk(tile_k, 128, row, cc, make_uint4(kk[4 * cc], kk[4 * cc + 1], kk[4 * cc + 2], kk[4 * cc + 3]));
+      fence_proxy_async_smem();
+      named_bar_sync(1, Cfg::NDT);
+      if (issuer) {
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) tma_store_4d(&tmdK, tile_k + cb * (128 * 128), cb * 64, h, kv0, b);
         tma_commit_group();
       }
     }
@@ -981,114 +1097,86 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ------------------------------- softmax warps -------------------------------
     const int quarter = warp & 3, grp = warp >> 2;   // TMEM lane quarter, query-column group
     const int row = quarter * 32 + lane;             // key row inside the tile == TMEM lane
-    const int kv_idx = kv0 + row;
     const int c0 = grp * CPT;                        // this thread's first query column
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sl2 = scale * kLog2e;
 
-    int s = 0;
+    int s = 0, g = 0;
     uint32_t qph = 0;
-    for (int it = 0; it < n_it; ++it) {
-      const uint32_t ph = it & 1;
-      const int q0 = kv0 + it * 64;
-      mbar_wait(&q_full[s], qph);                    // statistics of this tile are in shared memory
-      const float4* st_lse = reinterpret_cast<const float4*>(sStat + s * Cfg::STAT) + c0 / 4;
-      const float4* st_del = st_lse + 16;
-      float p[CPT];
-      // ---- Pᵀ = exp2(Sᵀ·c − lse·log2e)
-      mbar_wait(s_full, ph);
-      tc_fence_after();
-      {
-        uint32_t r[CPT];
-        tmem_ld_x32(t_lane + Cfg::ST_COL + c0, r);
-        tmem_ld_wait();
+    for (int ic = 0;; ++ic) {
+      const int w = next_item(ic);
+      if (w < 0) break;
+      int jt, h_, b_;
+      decode(w, jt, h_, b_);
+      const int kv0 = jt * 128, n_it = nq64 - 2 * jt;
+      const int kv_idx = kv0 + row;
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const uint32_t ph = g & 1;
+        const int q0 = kv0 + it * 64;
+        mbar_wait(&q_full[s], qph);                    // statistics of this tile are in shared memory
+        const float4* st_lse = reinterpret_cast<const float4*>(sStat + s * Cfg::STAT) + c0 / 4;
+        const float4* st_del = st_lse + 16;
+        float p[CPT];
+        // ---- Pᵀ = exp2(Sᵀ·c − lse·log2e)
+        mbar_wait(s_full, ph);
+        tc_fence_after();
+        {
+          uint32_t r[CPT];
+          tmem_ld_x32(t_lane + Cfg::ST_COL + c0, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < CPT / 4; ++g) {
-          const float4 l4 = st_lse[g];
-          p[4 * g] = exp2f(fmaf(__uint_as_float(r[4 * g]), sl2, -l4.x));
-          p[4 * g + 1] = exp2f(fmaf(__uint_as_float(r[4 * g + 1]), sl2, -l4.y));
-          p[4 * g + 2] = exp2f(fmaf(__uint_as_float(r[4 * g + 2]), sl2, -l4.z));
-          p[4 * g + 3] = exp2f(fmaf(__uint_as_float(r[4 * g + 3]), sl2, -l4.w));
+          for (int q4 = 0; q4 < CPT / 4; ++q4) {
+            const float4 l4 = st_lse[q4];
+            p[4 * q4] = exp2f(fmaf(__uint_as_float(r[4 * q4]), sl2, -l4.x));
+            p[4 * q4 + 1] = exp2f(fmaf(__uint_as_float(r[4 * q4 + 1]), sl2, -l4.y));
+            p[4 * q4 + 2] = exp2f(fmaf(__uint_as_float(r[4 * q4 + 2]), sl2, -l4.z));
+            p[4 * q4 + 3] = exp2f(fmaf(__uint_as_float(r[4 * q4 + 3]), sl2, -l4.w));
+          }
+          if (it < 2) {                                // the two 64-row tiles on the diagonal of this 128-key tile
+#pragma unroll
+            for (int e = 0; e < CPT; ++e)
+              if (kv_idx > q0 + c0 + e || kv_idx >= T) p[e] = 0.f;
+          }
+          uint32_t pk[CPT / 2];
+#pragma unroll
+          for (int e = 0; e < CPT / 2; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
+          tmem_st_x16(t_lane + Cfg::ST_COL + c0, pk);     // over this thread's own (already read) Sᵀ columns
+          tmem_st_wait();
         }
-        if (it < 2) {                                // the two 64-row tiles on the diagonal of this 128-key tile
+        tc_fence_before();
+        mbar_arrive(p_ready);
+        // ---- dSᵀ = Pᵀ ∘ (dPᵀ·scale − δ·scale)
+        mbar_wait(&dp_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        {
+          uint32_t d[CPT];
+          tmem_ld_x32(t_lane + Cfg::DPT_COL + (g & 1) * 64 + c0, d);
+          tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < CPT; ++e)
-            if (kv_idx > q0 + c0 + e || kv_idx >= T) p[e] = 0.f;
+          for (int q4 = 0; q4 < CPT / 4; ++q4) {
+            const float4 d4 = st_del[q4];
+            p[4 * q4] *= fmaf(__uint_as_float(d[4 * q4]), scale, -d4.x);
+            p[4 * q4 + 1] *= fmaf(__uint_as_float(d[4 * q4 + 1]), scale, -d4.y);
+            p[4 * q4 + 2] *= fmaf(__uint_as_float(d[4 * q4 + 2]), scale, -d4.z);
+            p[4 * q4 + 3] *= fmaf(__uint_as_float(d[4 * q4 + 3]), scale, -d4.w);
+          }
+          uint32_t pk[CPT / 2];
+#pragma unroll
+          for (int e = 0; e < CPT / 2; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
+          tmem_st_x16(t_lane + Cfg::DPT_COL + (g & 1) * 64 + c0, pk);
+          if (g > 0) mbar_wait(dq_full, ph ^ 1);       // dQᵀ(g-1) has retired: the (single) dSᵀ shared-memory tile may be overwritten
+          // the same values as the MN-major B tile of the dQᵀ product: row = key, 64 queries (128 bytes, swizzled) per row
+          uint8_t* rowp = sDS + row * 128;
+#pragma unroll
+          for (int q8 = 0; q8 < CPT / 8; ++q8)
+            *reinterpret_cast<uint4*>(rowp + (((c0 / 8 + q8) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q8], pk[4 * q8 + 1], pk[4 * q8 + 2], pk[4 * q8 + 3]);
+          tmem_st_wait();
         }
-        uint32_t pk[CPT / 2];
-#pragma unroll
-        for (int e = 0; e < CPT / 2; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
-        tmem_st_x16(t_lane + Cfg::ST_COL + c0, pk);     // over this thread's own (already read) Sᵀ columns
-        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(ds_ready);
+        if (++s == 3) { s = 0; qph ^= 1; }
       }
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      // ---- dSᵀ = Pᵀ ∘ (dPᵀ·scale − δ·scale)
-      mbar_wait(&dp_full[it & 1], (it >> 1) & 1);
-      tc_fence_after();
-      {
-        uint32_t d[CPT];
-        tmem_ld_x32(t_lane + Cfg::DPT_COL + (it & 1) * 64 + c0, d);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < CPT / 4; ++g) {
-          const float4 d4 = st_del[g];
-          p[4 * g] *= fmaf(__uint_as_float(d[4 * g]), scale, -d4.x);
-          p[4 * g + 1] *= fmaf(__uint_as_float(d[4 * g + 1]), scale, -d4.y);
-          p[4 * g + 2] *= fmaf(__uint_as_float(d[4 * g + 2]), scale, -d4.z);
-          p[4 * g + 3] *= fmaf(__uint_as_float(d[4 * g + 3]), scale, -d4.w);
-        }
-        uint32_t pk[CPT / 2];
-#pragma unroll
-        for (int e = 0; e < CPT / 2; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
-        tmem_st_x16(t_lane + Cfg::DPT_COL + (it & 1) * 64 + c0, pk);
-        if (it > 0) mbar_wait(dq_full, ph ^ 1);    // dQᵀ(it-1) has retired: the (single) dSᵀ shared-memory tile may be overwritten
-        // the same values as the MN-major B tile of the dQᵀ product: row = key, 64 queries (128 bytes, swizzled) per row
-        uint8_t* rowp = sDS + row * 128;
-#pragma unroll
-        for (int g = 0; g < CPT / 8; ++g)
-          *reinterpret_cast<uint4*>(rowp + (((c0 / 8 + g) ^ (row & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(ds_ready);
-      if (++s == 3) { s = 0; qph ^= 1; }
-    }
-    // ---- epilogue: dV, dK (thread = key row x 64 columns) -> bf16 swizzled tiles in the (now idle) Q / dO stages -> TMA store,
-    //      which also clips key rows past T.  dq_full(last) covers every MMA of this CTA.
-    mbar_wait(dq_full, (n_it - 1) & 1);
-    tc_fence_after();
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      uint8_t* tile = which ? sdO : sQ;
-      const uint32_t col = (which ? Cfg::DK_COL : Cfg::DV_COL) + grp * 64;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t r[32];
-        tmem_ld_x32(t_lane + col + ch * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v4;
-          v4.x = pack_bf16(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
-          v4.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
-          v4.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-          v4.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-          st_swizzled_chunk(tile, 128, row, grp * 8 + ch * 4 + g, v4);
-        }
-      }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(2, Cfg::NST);
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-        tma_store_4d(&tmdV, sQ + cb * (128 * 128), cb * 64, h, kv0, b);
-        tma_store_4d(&tmdK, sdO + cb * (128 * 128), cb * 64, h, kv0, b);
-      }
-      tma_commit_group();
-      tma_wait_group<0>();
     }
   }
 
@@ -1134,6 +1222,20 @@ void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, 
   check("attn_fwd");
 }
 
+// Two ints per device for the backward kernel's work distribution (next item, finished CTAs); zero between launches -- the
+// kernel re-arms them itself, so launches on one stream need no memset.  (Concurrent backward launches on different streams of
+// the same device would share them; the engine runs one compute stream.)
+static int* sched_counters() {
+  static int* ptrs[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!ptrs[dev]) {
+    if (cudaMalloc(&ptrs[dev], 2 * sizeof(int)) != cudaSuccess || cudaMemset(ptrs[dev], 0, 2 * sizeof(int)) != cudaSuccess)
+      throw std::runtime_error("attention: cannot allocate the scheduler counters");
+  }
+  return ptrs[dev];
+}
+
 void attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* delta, void* dq,
               void* dk, void* dv, float* dq_accum, int B, int T, int H, int C, long long q_row_stride, long long k_row_stride,
               long long v_row_stride, long long dqkv_row_stride, int num_sms, cudaStream_t s) {
@@ -1160,7 +1262,9 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
     CUtensorMap tdk = make_tmap_bthc(dk, B, T, H, C, dqkv_row_stride, 128), tdv = make_tmap_bthc(dv, B, T, H, C, dqkv_row_stride, 128);
     static bool once = (set_smem(attn_bwd3_kernel, Bwd3Cfg::SMEM), true);
     (void)once;
-    attn_bwd3_kernel<<<grid, Bwd3Cfg::THREADS, Bwd3Cfg::SMEM, s>>>(tq64, tk, tv, tdo64, tdq64, tdk, tdv, delta + 2 * plane, delta + plane, T, H, scale, dbg);
+    const int n_items = static_cast<int>(grid.x) * H * B;         // persistent: one CTA per SM pulls items off a global counter
+    attn_bwd3_kernel<<<std::min(num_sms, n_items), Bwd3Cfg::THREADS, Bwd3Cfg::SMEM, s>>>(tq64, tk, tv, tdo64, tdq64, tdk, tdv, delta + 2 * plane, delta + plane,
+                                                                                      T, H, n_items, sched_counters(), scale, dbg);
   } else if (C == 64) {
     static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
     (void)once;
