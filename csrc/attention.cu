@@ -885,12 +885,6 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (++s == 3) { s = 0; qph ^= 1; }
         }
       }
-      // the last CTA to run out of work re-arms the counters for the next launch (they start at zero)
-      if (atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
-        sched[1] = 0;
-        __threadfence();
-        sched[0] = 0;
-      }
     }
   } else if (warp == W_MMA) {
     // ------------------------------- MMA issuer -------------------------------
@@ -1222,17 +1216,14 @@ void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, 
   check("attn_fwd");
 }
 
-// Two ints per device for the backward kernel's work distribution (next item, finished CTAs); zero between launches -- the
-// kernel re-arms them itself, so launches on one stream need no memset.  (Concurrent backward launches on different streams of
-// the same device would share them; the engine runs one compute stream.)
-static int* sched_counters() {
+// Work counter of the backward kernel (one int per device, zeroed on the launch stream before every launch; launches of one
+// device are stream-ordered in this engine, so one counter per device is enough).
+static int* sched_counter(cudaStream_t s) {
   static int* ptrs[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!ptrs[dev]) {
-    if (cudaMalloc(&ptrs[dev], 2 * sizeof(int)) != cudaSuccess || cudaMemset(ptrs[dev], 0, 2 * sizeof(int)) != cudaSuccess)
-      throw std::runtime_error("attention: cannot allocate the scheduler counters");
-  }
+  if (!ptrs[dev] && cudaMalloc(&ptrs[dev], sizeof(int)) != cudaSuccess) throw std::runtime_error("attention: cannot allocate the work counter");
+  if (cudaMemsetAsync(ptrs[dev], 0, sizeof(int), s) != cudaSuccess) throw std::runtime_error("attention: cannot reset the work counter");
   return ptrs[dev];
 }
 
@@ -1264,7 +1255,7 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
     (void)once;
     const int n_items = static_cast<int>(grid.x) * H * B;         // persistent: one CTA per SM pulls items off a global counter
     attn_bwd3_kernel<<<std::min(num_sms, n_items), Bwd3Cfg::THREADS, Bwd3Cfg::SMEM, s>>>(tq64, tk, tv, tdo64, tdq64, tdk, tdv, delta + 2 * plane, delta + plane,
-                                                                                      T, H, n_items, sched_counters(), scale, dbg);
+                                                                                      T, H, n_items, sched_counter(s), scale, dbg);
   } else if (C == 64) {
     static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
     (void)once;
