@@ -10,10 +10,14 @@
 //              rescaling of the O accumulator *in TMEM*, P written as bf16 into 128B-swizzled smem
 //   warp 4     TMA producer (Q once, K/V double buffered)
 //   warp 5     tcgen05.mma issuer:  S = Q·Kᵀ (SS, fp32 in TMEM),  O += P·V (P K-major smem, V MN-major smem)
-// Backward (one CTA = one (batch, head, 128-key tile), loops over the query tiles at or below the diagonal)
+// Backward: work item = one (batch, head, 128-key tile), looping over the query tiles at or below the diagonal
 //   S = Q·Kᵀ, dP = dO·Vᵀ  →  P = exp2(S·c − lse), dS = P∘(dP − δ)/√C  →  dV += Pᵀ·dO, dK += dSᵀ·Q (TMEM-resident
-//   accumulators), dQ = dS·K is produced per tile in TMEM (aliasing S) and reduced into an fp32 buffer with
-//   vector atomics.  Every operand tile is loaded once and used through both K-major and MN-major descriptors.
+//   accumulators), dQ = dS·K per tile in TMEM, reduced into an fp32 buffer with TMA reduce-add.
+//   v3 (head_dim 128, T % 64 == 0; see the block comment at attn_bwd3_kernel): transposed scores, Pᵀ/dSᵀ as tensor-memory
+//      A operands, 64-row query tiles, dedicated output warps, persistent CTAs with dynamic work distribution.
+//   v2 (attn_bwd_kernel; head_dim 64, ragged T, MIDGPT_ATTN_BWD=v2): 128-row query tiles, one CTA per item, dQ aliases dP.
+// In every kernel the MMA-issuing warp runs converged with one elected lane per MMA group and hoisted descriptors
+// (common.cuh: desc_shift) -- otherwise the issuing thread, not the tensor core, sets the pace.
 #include "common.cuh"
 
 #include <algorithm>
