@@ -65,7 +65,7 @@ struct GemmParams {
   int accumulate;
   GatherParams ag;
   int group_m;                      // rasterisation: m-blocks per group (groups sweep all n-blocks), chosen on the host
-  int split_k;                      // > 1 only for the reduce-add fp32 epilogue (wgrad): K is cut into slices that add into D
+  int split_k;                      // != 1 only for the reduce-add fp32 epilogue (wgrad): hybrid stream-K schedule (see WorkIter)
   __nv_bfloat16* d2;                // EPI_GELU: second output (gelu(pre)), written with direct 16-byte stores
   long long ldd2;
   const float* row_scale_a;         // FP8 only: de-quantisation multipliers, one per row of A (token) …
@@ -83,6 +83,39 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
 // CG2 = true: CTA-pair kernel (cluster 2x1x1, tcgen05 cta_group::2).  A pair owns a 256 x 256 output tile: each CTA loads its
 // 128 rows of A and HALF of the B tile (128 rows), the leader issues M = 256 MMAs that read both CTAs' smem, each CTA's TMEM
 // receives its 128 accumulator rows.  Per-SM smem traffic for B and the L2 -> SM traffic for B halve; 6 stages instead of 4.
+// Work list of one worker (a CTA, or a CTA pair).  Plain mode: whole tiles worker, worker + n, ... (grouped rasterisation
+// keeps the tiles of a wave next to each other).  Hybrid stream-K (accumulating fp32 epilogue = wgrad, where the output has
+// only 64-256 tiles but K = #tokens is huge): the full waves are done the same way, then the k-blocks of the LEFTOVER tiles
+// are cut into equal contiguous ranges, one per worker; a range may span two tiles and every piece adds into D with the TMA
+// reduce-add the epilogue uses anyway.  All workers finish together and a tile is reduce-added 1-3 times instead of the
+// 3-10 times plain split-K needed for the same balance.
+struct WorkIter {
+  int n_workers, num_k, full_tiles;
+  int t;          // next whole tile
+  int u, u1;      // k-block units of the leftover tiles owned by this worker
+  MG_DEVICE WorkIter(int worker, int n_workers_, int tiles_mn, int num_k_, bool stream_k) : n_workers(n_workers_), num_k(num_k_) {
+    full_tiles = stream_k ? (tiles_mn / n_workers) * n_workers : tiles_mn;
+    const int units = (tiles_mn - full_tiles) * num_k;
+    const int per = (units + n_workers - 1) / n_workers;
+    if (worker < 0) { t = full_tiles; u = u1 = 0; return; }       // copy-engine CTAs own no tiles
+    t = worker;
+    u = min(units, worker * per);
+    u1 = min(units, u + per);
+  }
+  MG_DEVICE bool next(int& tile, int& kb0, int& kb1) {
+    if (t < full_tiles) { tile = t; kb0 = 0; kb1 = num_k; t += n_workers; return true; }
+    if (u < u1) {
+      const int lt = u / num_k;
+      tile = full_tiles + lt;
+      kb0 = u - lt * num_k;
+      kb1 = min(num_k, kb0 + (u1 - u));
+      u += kb1 - kb0;
+      return true;
+    }
+    return false;
+  }
+};
+
 template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false, bool CG2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -106,10 +139,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_m = CG2 ? (p.M + 2 * BM - 1) / (2 * BM) : (p.M + BM - 1) / BM;   // CG2: tiles are 256 rows tall
   const int num_n = (p.N + BN - 1) / BN;
   const int tiles_mn = num_m * num_n;
-  const int num_tiles = tiles_mn * p.split_k;       // work items: (k-slice, tile), slice-major
   constexpr int BKE = FP8 ? 2 * BK : BK;            // elements per k-block (a k-block is always 128 bytes per row)
   const int num_k_total = (p.K + BKE - 1) / BKE;
-  const int k_per_slice = (num_k_total + p.split_k - 1) / p.split_k;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -220,7 +251,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_pull = gather ? p.ag.n_ctas : 0;
   const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x) - n_pull;   // negative for copy-engine CTAs
   const int tile_stride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x) - n_pull;
-  const int my_first_tile = tile0 >= 0 ? tile0 : num_tiles;
+  const bool stream_k = p.split_k != 1;
 
   // tile -> (m_blk, n_blk).  With a fused gather the n-blocks are rotated so that locally-owned weight rows come first.
   const int n_rot = 0;   // segments land in address order, i.e. ascending weight rows: visit n-blocks in natural order
@@ -244,9 +275,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = my_first_tile; item < num_tiles; item += tile_stride) {
-        const int ks = item / tiles_mn, tile = item - ks * tiles_mn;
-        const int kb0 = ks * k_per_slice, kb1 = min(num_k_total, kb0 + k_per_slice);
+      WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, stream_k);
+      for (int tile, kb0, kb1; work.next(tile, kb0, kb1);) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         if (gather) {
@@ -317,9 +347,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int item = my_first_tile; item < num_tiles; item += tile_stride, ++it) {
-        const int ks = item / tiles_mn;
-        const int kb0 = ks * k_per_slice, kb1 = min(num_k_total, kb0 + k_per_slice);
+      WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, stream_k);
+      for (int tile, kb0, kb1; work.next(tile, kb0, kb1); ++it) {
         const int buf = it & 1;
         const uint32_t tphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[buf], tphase ^ 1);
@@ -350,13 +379,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        if (kb0 >= kb1) {                                  // empty K slice (never produced by pick_split_k): still hand the buffer on
-          if (elect_one()) {
-            if (CG2) umma_commit_mc2(&tfull_bar[buf]);
-            else umma_commit(&tfull_bar[buf]);
-          }
-          __syncwarp();
-        }
       }
     }
   } else {
@@ -367,8 +389,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool issuer = (threadIdx.x == 64);      // first epilogue thread issues the TMA stores
     const uint32_t sw = (row & 7);
     int it = 0;
-    for (int item = my_first_tile; item < num_tiles; item += tile_stride, ++it) {
-      const int tile = item % tiles_mn;
+    WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, stream_k);
+    for (int tile, kb0_, kb1_; work.next(tile, kb0_, kb1_); ++it) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int buf = it & 1;
@@ -554,16 +576,14 @@ static int pick_group_m(int N, int num_sms) {
   return g;
 }
 
-// Split-K for the accumulating fp32 epilogue (wgrad): the output has few tiles (e.g. 64–256 for the 1.5B layers) but K = #tokens is
-// huge, so whole waves are lost to quantisation; slices of K add into D with the same TMA reduce-add the epilogue uses anyway.
+// Hybrid stream-K (see WorkIter) for the accumulating fp32 epilogue whenever the tile count is not a multiple of the worker
+// count and K is long enough for the extra partial epilogues to be noise (>= 16 k-blocks per worker in the split part).
 static int pick_split_k(int tiles, int workers, int num_k, int epi, int accumulate) {
-  if (epi != EPI_F32 || !accumulate || tiles >= 8 * workers) return 1;
-  int s = (8 * workers + tiles - 1) / tiles;
-  const int max_s = num_k / 16 > 0 ? num_k / 16 : 1;     // keep >= 16 k-blocks (1024 tokens) per slice
-  if (s > max_s) s = max_s;
-  if (s < 1) s = 1;
-  const int kps = (num_k + s - 1) / s;          // k-blocks per slice as the kernel computes it …
-  return (num_k + kps - 1) / kps;               // … and the number of NON-EMPTY slices that yields
+  if (epi != EPI_F32 || !accumulate) return 1;
+  const int leftover = tiles % workers;
+  if (leftover == 0) return 1;
+  const long long units = static_cast<long long>(leftover) * num_k;
+  return units >= 16ll * workers ? 2 : 1;
 }
 
 static int g_use_cg2 = -1;      // CTA-pair kernels for the plain bf16 GEMMs (MIDGPT_GEMM_2CTA=0 disables)
@@ -585,9 +605,9 @@ static void launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUte
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(pair): ") + cudaGetErrorString(e));
     configured = true;
   }
-  const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN) * p.split_k;
+  const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
   int pairs = num_sms / 2;
-  if (num_tiles < pairs) pairs = num_tiles;
+  if (p.split_k == 1 && num_tiles < pairs) pairs = num_tiles;     // stream-K always uses every pair
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -611,8 +631,8 @@ static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.split_k;
-  int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  int grid = (p.split_k == 1 && num_tiles < num_sms) ? num_tiles : num_sms;     // stream-K always uses every SM
   if (AG && p.ag.n_ctas > 0) {                      // copy-engine CTAs come on top of the GEMM workers (all co-resident: 1 CTA / SM)
     const int workers = num_tiles < num_sms - p.ag.n_ctas ? num_tiles : num_sms - p.ag.n_ctas;
     grid = workers + p.ag.n_ctas;

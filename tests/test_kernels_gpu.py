@@ -67,6 +67,20 @@ def test_gemm_dgrad_and_wgrad(be, ref, M, N, K):
     assert rel_err(acc, want + dy.float().t() @ x.float()) < 3e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(8192, 1024, 768), (16384, 2560, 2048)])
+def test_gemm_wgrad_stream_k(be, M, N, K):
+    """Long-K weight gradients take the hybrid stream-K schedule (csrc/gemm.cu WorkIter): fewer tiles than workers (12 on 74
+    CTA pairs) and one full wave + 6 leftover tiles; every partial piece must add into the fp32 accumulator exactly once."""
+    torch.manual_seed(21)
+    dy, x = rnd(M, N), rnd(M, K)
+    acc = torch.randn(N, K, device="cuda")
+    want = acc.double() + dy.double().t() @ x.double()
+    be.linear_wgrad(dy, x, acc)
+    assert rel_err(acc, want) < 2e-3
+    be.linear_wgrad(dy, x, acc)
+    assert rel_err(acc, want + dy.double().t() @ x.double()) < 2e-3
+
+
 # ----------------------------------------------------------------------------------------------- element-wise
 @pytest.mark.parametrize("D", [384, 768, 2048])
 def test_rmsnorm(be, ref, D):
