@@ -65,7 +65,7 @@ struct GemmParams {
   int accumulate;
   GatherParams ag;
   int group_m;                      // rasterisation: m-blocks per group (groups sweep all n-blocks), chosen on the host
-  int split_k;                      // != 1 only for the reduce-add fp32 epilogue (wgrad): hybrid stream-K schedule (see WorkIter)
+  int split_k;                      // > 0 only for the reduce-add fp32 epilogue (wgrad): K-slices of the leftover tiles (see WorkIter)
   __nv_bfloat16* d2;                // EPI_GELU: second output (gelu(pre)), written with direct 16-byte stores
   long long ldd2;
   const float* row_scale_a;         // FP8 only: de-quantisation multipliers, one per row of A (token) …
@@ -83,33 +83,33 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
 // CG2 = true: CTA-pair kernel (cluster 2x1x1, tcgen05 cta_group::2).  A pair owns a 256 x 256 output tile: each CTA loads its
 // 128 rows of A and HALF of the B tile (128 rows), the leader issues M = 256 MMAs that read both CTAs' smem, each CTA's TMEM
 // receives its 128 accumulator rows.  Per-SM smem traffic for B and the L2 -> SM traffic for B halve; 6 stages instead of 4.
-// Work list of one worker (a CTA, or a CTA pair).  Plain mode: whole tiles worker, worker + n, ... (grouped rasterisation
-// keeps the tiles of a wave next to each other).  Hybrid stream-K (accumulating fp32 epilogue = wgrad, where the output has
-// only 64-256 tiles but K = #tokens is huge): the full waves are done the same way, then the k-blocks of the LEFTOVER tiles
-// are cut into equal contiguous ranges, one per worker; a range may span two tiles and every piece adds into D with the TMA
-// reduce-add the epilogue uses anyway.  All workers finish together and a tile is reduce-added 1-3 times instead of the
-// 3-10 times plain split-K needed for the same balance.
+// Work list of one worker (a CTA, or a CTA pair).  Plain mode (split == 0): whole tiles worker, worker + n, ... (grouped
+// rasterisation keeps the tiles of a wave next to each other in L2).  Hybrid split-K (accumulating fp32 epilogue = wgrad, where
+// the output has only 64-256 tiles but K = #tokens is huge): the full waves are done the same way, and only the LEFTOVER
+// tiles (fewer than one wave) are cut into `split` K-slices, handed out slice-major so that the workers running at any moment
+// share one k-range of neighbouring tiles in L2; every piece adds into D with the TMA reduce-add the epilogue uses anyway.
+// (Measured alternatives: plain split-K of ALL tiles reduce-adds every tile 3-10 times; equal contiguous k-ranges per worker
+// -- "stream-K" -- balance perfectly but share nothing in L2 and turned the 64-tile attn_proj wgrad HBM-bound, +44 %.)
 struct WorkIter {
-  int n_workers, num_k, full_tiles;
+  int n_workers, num_k, full_tiles, left, kps;
   int t;          // next whole tile
-  int u, u1;      // k-block units of the leftover tiles owned by this worker
-  MG_DEVICE WorkIter(int worker, int n_workers_, int tiles_mn, int num_k_, bool stream_k) : n_workers(n_workers_), num_k(num_k_) {
-    full_tiles = stream_k ? (tiles_mn / n_workers) * n_workers : tiles_mn;
-    const int units = (tiles_mn - full_tiles) * num_k;
-    const int per = (units + n_workers - 1) / n_workers;
-    if (worker < 0) { t = full_tiles; u = u1 = 0; return; }       // copy-engine CTAs own no tiles
-    t = worker;
-    u = min(units, worker * per);
-    u1 = min(units, u + per);
+  int i, n_items; // leftover items (slice-major): slice = i / left, tile = full_tiles + i % left
+  MG_DEVICE WorkIter(int worker, int n_workers_, int tiles_mn, int num_k_, int split) : n_workers(n_workers_), num_k(num_k_) {
+    full_tiles = split > 0 ? (tiles_mn / n_workers) * n_workers : tiles_mn;
+    left = tiles_mn - full_tiles;
+    kps = split > 0 ? (num_k + split - 1) / split : num_k;
+    n_items = left * (split > 0 ? (num_k + kps - 1) / kps : 0);       // only the non-empty slices
+    t = worker < 0 ? full_tiles : worker;                             // copy-engine CTAs (worker < 0) own no tiles
+    i = worker < 0 ? n_items : worker;
   }
   MG_DEVICE bool next(int& tile, int& kb0, int& kb1) {
     if (t < full_tiles) { tile = t; kb0 = 0; kb1 = num_k; t += n_workers; return true; }
-    if (u < u1) {
-      const int lt = u / num_k;
-      tile = full_tiles + lt;
-      kb0 = u - lt * num_k;
-      kb1 = min(num_k, kb0 + (u1 - u));
-      u += kb1 - kb0;
+    if (i < n_items) {
+      const int slice = i / left;
+      tile = full_tiles + (i - slice * left);
+      kb0 = slice * kps;
+      kb1 = min(num_k, kb0 + kps);
+      i += n_workers;
       return true;
     }
     return false;
@@ -251,7 +251,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_pull = gather ? p.ag.n_ctas : 0;
   const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x) - n_pull;   // negative for copy-engine CTAs
   const int tile_stride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x) - n_pull;
-  const bool stream_k = p.split_k != 1;
 
   // tile -> (m_blk, n_blk).  With a fused gather the n-blocks are rotated so that locally-owned weight rows come first.
   const int n_rot = 0;   // segments land in address order, i.e. ascending weight rows: visit n-blocks in natural order
@@ -275,7 +274,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, stream_k);
+      WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, p.split_k);
       for (int tile, kb0, kb1; work.next(tile, kb0, kb1);) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
@@ -347,7 +346,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, stream_k);
+      WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, p.split_k);
       for (int tile, kb0, kb1; work.next(tile, kb0, kb1); ++it) {
         const int buf = it & 1;
         const uint32_t tphase = (it >> 1) & 1;
@@ -389,7 +388,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool issuer = (threadIdx.x == 64);      // first epilogue thread issues the TMA stores
     const uint32_t sw = (row & 7);
     int it = 0;
-    WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, stream_k);
+    WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, p.split_k);
     for (int tile, kb0_, kb1_; work.next(tile, kb0_, kb1_); ++it) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
@@ -576,14 +575,21 @@ static int pick_group_m(int N, int num_sms) {
   return g;
 }
 
-// Hybrid stream-K (see WorkIter) for the accumulating fp32 epilogue whenever the tile count is not a multiple of the worker
-// count and K is long enough for the extra partial epilogues to be noise (>= 16 k-blocks per worker in the split part).
+// K-slices for the leftover tiles of the accumulating fp32 epilogue (see WorkIter); 0 = plain whole-tile schedule.
+// Cost model in k-block units: waves x (slice length + one epilogue ~ 8 k-blocks); slices keep >= 16 k-blocks.
 static int pick_split_k(int tiles, int workers, int num_k, int epi, int accumulate) {
-  if (epi != EPI_F32 || !accumulate) return 1;
-  const int leftover = tiles % workers;
-  if (leftover == 0) return 1;
-  const long long units = static_cast<long long>(leftover) * num_k;
-  return units >= 16ll * workers ? 2 : 1;
+  if (epi != EPI_F32 || !accumulate) return 0;
+  const int left = tiles % workers;
+  if (left == 0) return 1;
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= 16 && (s == 1 || num_k / s >= 16); ++s) {
+    const int kps = (num_k + s - 1) / s, slices = (num_k + kps - 1) / kps;
+    const long long waves = (static_cast<long long>(left) * slices + workers - 1) / workers;
+    const long long cost = waves * (kps + 8);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 static int g_use_cg2 = -1;      // CTA-pair kernels for the plain bf16 GEMMs (MIDGPT_GEMM_2CTA=0 disables)
@@ -607,7 +613,7 @@ static void launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUte
   }
   const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
   int pairs = num_sms / 2;
-  if (p.split_k == 1 && num_tiles < pairs) pairs = num_tiles;     // stream-K always uses every pair
+  if (num_tiles * (p.split_k > 0 ? p.split_k : 1) < pairs) pairs = num_tiles * (p.split_k > 0 ? p.split_k : 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -632,7 +638,7 @@ static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     configured = true;
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  int grid = (p.split_k == 1 && num_tiles < num_sms) ? num_tiles : num_sms;     // stream-K always uses every SM
+  int grid = num_tiles * (p.split_k > 0 ? p.split_k : 1) < num_sms ? num_tiles * (p.split_k > 0 ? p.split_k : 1) : num_sms;
   if (AG && p.ag.n_ctas > 0) {                      // copy-engine CTAs come on top of the GEMM workers (all co-resident: 1 CTA / SM)
     const int workers = num_tiles < num_sms - p.ag.n_ctas ? num_tiles : num_sms - p.ag.n_ctas;
     grid = workers + p.ag.n_ctas;

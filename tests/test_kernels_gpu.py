@@ -68,9 +68,9 @@ def test_gemm_dgrad_and_wgrad(be, ref, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(8192, 1024, 768), (16384, 2560, 2048)])
-def test_gemm_wgrad_stream_k(be, M, N, K):
-    """Long-K weight gradients take the hybrid stream-K schedule (csrc/gemm.cu WorkIter): fewer tiles than workers (12 on 74
-    CTA pairs) and one full wave + 6 leftover tiles; every partial piece must add into the fp32 accumulator exactly once."""
+def test_gemm_wgrad_hybrid_split_k(be, M, N, K):
+    """Long-K weight gradients take the hybrid split-K schedule (csrc/gemm.cu WorkIter): fewer tiles than workers (12 on 74
+    CTA pairs) and one full wave + 6 leftover tiles cut into K-slices; every piece must add into the fp32 accumulator exactly once."""
     torch.manual_seed(21)
     dy, x = rnd(M, N), rnd(M, K)
     acc = torch.randn(N, K, device="cuda")
