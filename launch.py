@@ -42,7 +42,6 @@ def parse_args(argv=None):
 
 
 def apply_overrides(config, pairs):
-    import dataclasses
     for kv in pairs:
         k, v = kv.split("=", 1)
         obj = config

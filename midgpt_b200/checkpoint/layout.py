@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import typing as tp
 
-from ..config import ExperimentConfig
 
 # (key, kind, source) — kind "array": source is a reference-leaf name (models/params.py);
 # kind "scalar": source is a callable(cfg) → python scalar.

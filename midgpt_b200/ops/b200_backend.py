@@ -9,7 +9,6 @@ GEMM operand conventions (csrc/gemm.cu): ``ext.gemm(a, a_mn, b, b_mn, d, epi, d2
 from __future__ import annotations
 
 import importlib.util
-import math
 import os
 import typing as tp
 

@@ -27,7 +27,7 @@ world > 8 → HSDP: reduce-scatter inside the 8-rank shard group, all-reduce acr
 from __future__ import annotations
 
 import typing as tp
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import torch
 

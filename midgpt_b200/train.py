@@ -13,17 +13,14 @@ manager → optimizer → sharded init → resume → loop {eval every ``eval_in
 from __future__ import annotations
 
 import math
-import os
-import time
 import typing as tp
 
-import numpy as np
 import torch
 
 from .config import ExperimentConfig
 from .data import BatchSampler, PinnedBatchLoader, load_tokens, split_array_by_idx, synthetic_tokens, dataset_available
 from .models.gpt import GPTModel
-from .models.params import count_params, flops_per_token
+from .models.params import count_params
 from .ops import get_backend
 from .parallel import dist as D
 from .parallel.fsdp import FSDPEngine

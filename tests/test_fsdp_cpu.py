@@ -1,5 +1,4 @@
 """FSDP (gloo, world_size=2, CPU) ≡ single process: losses and post-step parameters (BASELINE config 1 plumbing)."""
-import dataclasses
 
 import pytest
 import torch

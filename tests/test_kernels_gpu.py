@@ -1,5 +1,4 @@
 """Numerics of every hand-written sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
-import math
 
 import pytest
 import torch
