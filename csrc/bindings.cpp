@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 namespace mg {
+std::vector<int> gemm_work_plan(int M, int N, int K, int epi, int accumulate, int num_sms, bool pairs);
 void gemm_launch(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d, long long ldd,
                  void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int accumulate,
                  int num_sms, cudaStream_t stream);
@@ -331,6 +332,8 @@ void ag_pull(std::vector<int64_t> lp_ptrs, at::Tensor& local, int64_t shard_elem
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM with fused epilogues");
+  m.def("gemm_work_plan", [](int M, int N, int K, int epi, int accumulate, int num_sms, bool pairs) { return mg::gemm_work_plan(M, N, K, epi, accumulate, num_sms, pairs); },
+        "host replay of the GEMM tile / K-slice schedule: flat list of (worker, tile, kb0, kb1)");
   m.def("gemm_ag", &gemm_ag, "all-gather (NVLink pull) fused with the tcgen05 GEMM");
   m.def("quant_rows_e4m3", &quant_rows_e4m3);
   m.def("quant_mx_e4m3", &quant_mx_e4m3);

@@ -21,6 +21,7 @@
 #include <mutex>
 #include <tuple>
 #include <stdexcept>
+#include <vector>
 #include <string>
 
 namespace mg {
@@ -94,7 +95,7 @@ struct WorkIter {
   int n_workers, num_k, full_tiles, left, kps;
   int t;          // next whole tile
   int i, n_items; // leftover items (slice-major): slice = i / left, tile = full_tiles + i % left
-  MG_DEVICE WorkIter(int worker, int n_workers_, int tiles_mn, int num_k_, int split) : n_workers(n_workers_), num_k(num_k_) {
+  __host__ MG_DEVICE WorkIter(int worker, int n_workers_, int tiles_mn, int num_k_, int split) : n_workers(n_workers_), num_k(num_k_) {
     full_tiles = split > 0 ? (tiles_mn / n_workers) * n_workers : tiles_mn;
     left = tiles_mn - full_tiles;
     kps = split > 0 ? (num_k + split - 1) / split : num_k;
@@ -102,13 +103,13 @@ struct WorkIter {
     t = worker < 0 ? full_tiles : worker;                             // copy-engine CTAs (worker < 0) own no tiles
     i = worker < 0 ? n_items : worker;
   }
-  MG_DEVICE bool next(int& tile, int& kb0, int& kb1) {
+  __host__ MG_DEVICE bool next(int& tile, int& kb0, int& kb1) {
     if (t < full_tiles) { tile = t; kb0 = 0; kb1 = num_k; t += n_workers; return true; }
     if (i < n_items) {
       const int slice = i / left;
       tile = full_tiles + (i - slice * left);
       kb0 = slice * kps;
-      kb1 = min(num_k, kb0 + kps);
+      kb1 = kb0 + kps < num_k ? kb0 + kps : num_k;
       i += n_workers;
       return true;
     }
@@ -751,6 +752,25 @@ void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb,
   if (epi == EPI_GELU) return launch_one<false, false, EPI_GELU, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
   if (epi == EPI_RESIDUAL) return launch_one<false, false, EPI_RESIDUAL, false, true>(tA, tB, tD, tD2, p, num_sms, stream);
   throw std::runtime_error("gemm_fp8: unsupported epilogue");
+}
+
+// The work plan of a GEMM exactly as the kernel will walk it (pick_split_k + WorkIter run on the host): one row
+// (worker, tile, kb0, kb1) per piece.  Used by the CPU tests to check that every (tile, k-block) is covered exactly once.
+std::vector<int> gemm_work_plan(int M, int N, int K, int epi, int accumulate, int num_sms, bool pairs) {
+  const int tiles = pairs ? ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN) : ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int num_k = (K + BK - 1) / BK;
+  const int max_workers = pairs ? num_sms / 2 : num_sms;
+  const int split = pick_split_k(tiles, max_workers, num_k, epi, accumulate);
+  const int items = tiles * (split > 0 ? split : 1);
+  const int workers = items < max_workers ? items : max_workers;      // same rule as the launchers' grid size
+  std::vector<int> out;
+  for (int w = 0; w < workers; ++w) {
+    WorkIter it(w, workers, tiles, num_k, split);
+    for (int tile, kb0, kb1; it.next(tile, kb0, kb1);) {
+      out.push_back(w); out.push_back(tile); out.push_back(kb0); out.push_back(kb1);
+    }
+  }
+  return out;
 }
 
 }  // namespace mg
