@@ -7,9 +7,9 @@
 //
 // Forward  (one CTA = one (batch, head, 128-query tile); 2 CTAs co-reside per SM and fill each other's bubbles)
 //   warps 0-3  softmax: thread = one query row; S row read from TMEM, online max/sum with lazy (threshold)
-//              rescaling of the O accumulator *in TMEM*, P written as bf16 into 128B-swizzled smem
+//              rescaling of the O accumulator *in TMEM*, P written back as packed bf16 over its own S columns (tcgen05.st)
 //   warp 4     TMA producer (Q once, K/V double buffered)
-//   warp 5     tcgen05.mma issuer:  S = Q·Kᵀ (SS, fp32 in TMEM),  O += P·V (P K-major smem, V MN-major smem)
+//   warp 5     tcgen05.mma issuer:  S = Q·Kᵀ (SS, fp32 in TMEM),  O += P·V (P from tensor memory, V MN-major smem)
 // Backward: work item = one (batch, head, 128-key tile), looping over the query tiles at or below the diagonal
 //   S = Q·Kᵀ, dP = dO·Vᵀ  →  P = exp2(S·c − lse), dS = P∘(dP − δ)/√C  →  dV += Pᵀ·dO, dK += dSᵀ·Q (TMEM-resident
 //   accumulators), dQ = dS·K per tile in TMEM, reduced into an fp32 buffer with TMA reduce-add.
@@ -89,11 +89,12 @@ struct FwdCfg {
   static constexpr int Q_BYTES = BQ * C * 2;
   static constexpr int K_BYTES = BKV * C * 2;
   static constexpr int V_BYTES = BKV * C * 2;
-  static constexpr int P_BYTES = BQ * BKV * 2;
-  static constexpr int SMEM = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES + 256;
+  static constexpr int SMEM = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + 256;
   static constexpr int TMEM_COLS = 256;
-  static constexpr int S_COL = 0, O_COL = 2 * BKV;      // two S buffers (QK of tile j+1 overlaps the softmax of tile j), then O
+  static constexpr int S_COL = 0, O_COL = 2 * BKV;      // two S buffers (QK of tile j+1 overlaps the softmax of tile j), then O;
+                                                        // P_j (bf16, two per column) overwrites the first BKV/2 columns of S buffer j & 1
   static_assert(2 * BKV + C <= TMEM_COLS, "TMEM budget");
+  static_assert(BKV == 64, "P is packed over an S row that must already sit in registers (KEEP path)");
 };
 
 template <int C>
@@ -109,8 +110,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + 2 * Cfg::K_BYTES;
-  uint8_t* sP = sV + 2 * Cfg::V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Cfg::V_BYTES);
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // 2
   uint64_t* k_empty = bars + 3;       // 2
@@ -166,7 +166,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, C, 0, 1);
       // descriptors are built once; per MMA only a 64-bit add of a compile-time offset (see desc_shift)
-      const uint64_t q_desc = make_smem_desc(smem_u32(sQ), 16, 1024), p_desc = make_smem_desc(smem_u32(sP), 16, 1024);
+      const uint64_t q_desc = make_smem_desc(smem_u32(sQ), 16, 1024);
       const uint64_t k_desc0 = make_smem_desc(smem_u32(sK), 16, 1024), v_desc0 = make_smem_desc(smem_u32(sV), BKV * 128, 1024);
       auto issue_qk = [&](int j) {
         const int st = j & 1;
@@ -189,7 +189,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_qk(0);
       if (n_kv > 1) issue_qk(1);           // S is double buffered: the next QKᵀ never waits for the softmax
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(p_full, j & 1);          // P_j is in smem and S_j has been fully read
+        mbar_wait(p_full, j & 1);          // P_j is in tensor memory (over the S_j columns every thread has already read)
         tc_fence_after();
         const int st = j & 1;
         mbar_wait(&v_full[st], (j >> 1) & 1);
@@ -197,10 +197,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint64_t v_desc = desc_shift(v_desc0, st * Cfg::V_BYTES);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            const uint32_t blk = (k * 16) / 64, in = (k * 16) % 64;
-            umma_bf16_ss(tmem + Cfg::O_COL, desc_shift(p_desc, blk * (BQ * 128) + in * 2), desc_shift(v_desc, k * 2048), idesc_o, (j | k) != 0);
-          }
+          for (int k = 0; k < BKV / 16; ++k)       // A = P_j straight from TMEM: 16 keys = 8 packed columns per k-step
+            umma_bf16_ts(tmem + Cfg::O_COL, tmem + Cfg::S_COL + st * BKV + k * 8, desc_shift(v_desc, k * 2048), idesc_o, (j | k) != 0);
           umma_commit(&v_empty[st]);
           umma_commit(pv_done);
         }
@@ -258,10 +256,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       mx *= sl2;                                             // sl2 > 0: max commutes with the scaling
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);           // O_{j-1} complete; P buffer free
-        tc_fence_after();
         const bool need = mx > m_used + 8.f;       // lazy rescale: only when the max grew by > 2^8
         if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(pv_done, (j - 1) & 1);         // O_{j-1} complete (P_{j-1} lives in the other S buffer: nothing else to wait for)
+          tc_fence_after();
           const float alpha = need ? exp2f(m_used - mx) : 1.f;
           if (need) m_used = mx;
           l *= alpha;
@@ -279,7 +277,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else {
         m_used = mx;
       }
-      // pass 2: P = exp2(s*c - m_used) -> bf16 -> swizzled smem (K-major A operand of P·V)
+      // pass 2: P = exp2(s*c - m_used) -> bf16, packed two per column, back into this thread's lane of S buffer j & 1
+      //         (tensor-memory A operand of P·V; the whole S row is already in registers)
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         uint32_t tmp[32];
@@ -304,15 +303,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             l += p[e];
           }
         }
+        uint32_t pk[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v4 = make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
-                                pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7]));
-          st_swizzled_chunk(sP, BQ, row, ch * 4 + g, v4);
-        }
+        for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
+        tmem_st_x16(t_lane + s_col + ch * 16, pk);
       }
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
       mbar_arrive(p_full);
     }
     // epilogue: O / l -> bf16 -> global ; lse
