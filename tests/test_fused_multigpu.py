@@ -54,3 +54,48 @@ def test_fused_comm_matches_nccl(gather_mode):
             err = (torch.as_tensor(sf[k]) - torch.as_tensor(sn[k])).norm() / (torch.as_tensor(sn[k]).norm() + 1e-9)
             assert err < 2e-3, (k, err.item())
     assert nccl[0][0][-1] < nccl[0][0][0]
+
+
+def _flag_stress(rank, world, iters):
+    """Every iteration: stamp the local symmetric buffer, device barrier, read EVERY peer's buffer over NVLink and check its stamp,
+    device barrier again (so nobody overwrites a buffer that is still being read).  Random per-rank spin kernels in between
+    shake the relative timing of the ranks; a lost release/acquire or an epoch mix-up shows up as a stale stamp."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+    from midgpt_b200.ops.b200_backend import B200Backend
+    from midgpt_b200.parallel.dist import init_distributed
+    rank, world, local, dev, _ = init_distributed("cuda")
+    be = B200Backend(dev)
+    n = 1 << 16
+    buf = symm.empty(n, dtype=torch.int32, device=dev)
+    pad = symm.empty(1024, dtype=torch.int32, device=dev)
+    buf.zero_(); pad.zero_()
+    h_buf, h_pad = symm.rendezvous(buf, dist.group.WORLD), symm.rendezvous(pad, dist.group.WORLD)
+    peers = [h_buf.get_buffer(p, (n,), torch.int32) for p in range(world)]
+    pads = [int(p) for p in h_pad.buffer_ptrs]
+    torch.cuda.synchronize()
+    dist.barrier()
+    g = torch.Generator().manual_seed(100 + rank)
+    bad = torch.zeros((), dtype=torch.int64, device=dev)
+    epoch = 0
+    for it in range(iters):
+        if torch.rand((), generator=g).item() < 0.5:
+            torch.cuda._sleep(int(torch.randint(1, 200_000, (), generator=g)))
+        buf.fill_(it * 16 + rank)
+        epoch += 1
+        be.ext.xrank_barrier(pads, rank, 1, epoch)
+        for p in range(world):
+            bad += (peers[p] != it * 16 + p).sum()
+        epoch += 1
+        be.ext.xrank_barrier(pads, rank, 1, epoch)
+    torch.cuda.synchronize()
+    return int(bad.item())
+
+
+def test_device_barrier_flag_protocol_stress():
+    """signal/flag-protocol stress test for the in-kernel P2P paths (csrc/comm.cu xrank_barrier)."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("not enough GPUs")
+    out = run_distributed(_flag_stress, world, 300, timeout=300)
+    assert out == [0] * world, out
