@@ -95,23 +95,32 @@ def main(argv=None):
     apply_overrides(config, args.set)
 
     wandb_id = None
+    from midgpt_b200.utils.remote import RemoteDir, is_remote
+    remote = RemoteDir(config.rundir) if (not args.debug and is_remote(config.rundir)) else None
     if rank == 0 and not args.debug:
         print(f"Writing to {config.rundir}")
-        if config.rundir.startswith("gs://"):
-            raise SystemExit("gs:// rundirs need gcsfs, which is not available in this image; use a local/NFS path")
-        print("Using local filesystem")
-        config.rundir = os.path.abspath(config.rundir)
-        os.makedirs(config.rundir, exist_ok=True)
-        with open(os.path.join(config.rundir, "config.json"), "w") as f:
+        if remote is not None:          # reference: gcsfs for gs:// paths (launch.py:43-50); here any fsspec scheme, via a local mirror
+            print(f"Using remote filesystem ({config.rundir.split('://', 1)[0]}://), local mirror {remote.local}")
+            local_dir = remote.local
+            remote.pull_file("wandb_id.txt")
+        else:
+            print("Using local filesystem")
+            config.rundir = os.path.abspath(config.rundir)
+            local_dir = config.rundir
+        os.makedirs(local_dir, exist_ok=True)
+        with open(os.path.join(local_dir, "config.json"), "w") as f:
             f.write(config_to_json(config))
-        wid_path = os.path.join(config.rundir, "wandb_id.txt")
+        wid_path = os.path.join(local_dir, "wandb_id.txt")
         if os.path.exists(wid_path):
             wandb_id = open(wid_path).read().strip()
         else:
             wandb_id = uuid.uuid4().hex[:8]
             with open(wid_path, "w") as f:
                 f.write(wandb_id)
-    elif not args.debug:
+        if remote is not None:
+            remote.push_file("config.json")
+            remote.push_file("wandb_id.txt")
+    elif not args.debug and remote is None:
         config.rundir = os.path.abspath(config.rundir)
 
     trainer = Trainer(config, device_type=args.device)

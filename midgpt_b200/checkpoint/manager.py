@@ -42,7 +42,10 @@ TMP_SUFFIX = ".orbax-checkpoint-tmp"
 
 class CheckpointManager:
     def __init__(self, directory: str, max_to_keep: int | None = 1, save_interval_steps: int = 1,
-                 async_save: bool = True):
+                 async_save: bool = True, remote=None):
+        """``remote``: a ``utils.remote.RemoteDir`` whose local mirror is ``directory`` — committed steps are pushed to it
+        (rank 0, from the commit thread) and ``sync_from_remote`` pulls the newest one before a resume."""
+        self.remote = remote
         self.dir = os.path.abspath(directory)
         self.max_to_keep, self.interval, self.async_save = max_to_keep, max(1, save_interval_steps), async_save
         self._thread: threading.Thread | None = None
@@ -60,6 +63,15 @@ class CheckpointManager:
     def latest_step(self) -> int | None:
         s = self.all_steps()
         return s[-1] if s else None
+
+    def sync_from_remote(self, mesh) -> None:
+        """Make the newest remote step available in the local mirror (one rank per node downloads; collective when world > 1)."""
+        if self.remote is None:
+            return
+        if mesh.local_rank == 0:
+            self.remote.pull_latest_step()
+        if mesh.world > 1:
+            torch.distributed.barrier()
 
     def should_save(self, step: int) -> bool:
         return step % self.interval == 0
@@ -141,6 +153,9 @@ class CheckpointManager:
                         shutil.rmtree(final)
                     os.replace(tmp, final)
                     self._prune()
+                    if self.remote is not None:
+                        self.remote.push_step(step, self.max_to_keep)
+                        self.remote.push_file("metrics.jsonl")
             except BaseException as e:  # surfaced by wait_until_finished
                 self._error = e
 

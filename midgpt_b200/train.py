@@ -137,9 +137,15 @@ class Trainer:
             print(f"[engine] world={m.world} shard_group={m.shard_size} replicas={m.replica_size} backend={self.backend.name} "
                   f"comm={eng.comm} gather={eng.gather_mode} micro_bs={self.micro_bs}x{self.n_micro} remat={cfg.engine.remat}")
         mngr = None
+        remote, local_rundir = None, cfg.rundir
         if not cfg.debug and cfg.rundir:
-            mngr = CheckpointManager(cfg.rundir, max_to_keep=1, save_interval_steps=cfg.eval_interval,
-                                     async_save=cfg.engine.ckpt_async)
+            from .utils.remote import RemoteDir, is_remote
+            if is_remote(cfg.rundir):        # object-store run directory: work in the local mirror, push committed steps
+                remote = RemoteDir(cfg.rundir)
+                local_rundir = remote.local
+            mngr = CheckpointManager(local_rundir, max_to_keep=1, save_interval_steps=cfg.eval_interval,
+                                     async_save=cfg.engine.ckpt_async, remote=remote)
+            mngr.sync_from_remote(m)
         first_step = 0
         if mngr is not None and mngr.latest_step() is not None:
             extra = mngr.restore(mngr.latest_step(), eng)
@@ -148,9 +154,9 @@ class Trainer:
                 train_s.load_state_dict(extra["sampler"])
             if m.is_main:
                 print(f"[ckpt] resumed from step {first_step - 1}")
-        logger = obs.MetricLogger(cfg.rundir or None, cfg.reference_dict(), enabled=m.is_main,
+        logger = obs.MetricLogger(local_rundir or None, cfg.reference_dict(), enabled=m.is_main,
                                   wandb_id=getattr(self, "wandb_id", None))
-        prof = obs.DebugProfiler(cfg.rundir or ".", m.rank) if cfg.debug else None
+        prof = obs.DebugProfiler(local_rundir or ".", m.rank) if cfg.debug else None
         loader = PinnedBatchLoader(train_s, self.local_seqs, m.device)
         timer = obs.StepTimer(m.device)
         total = cfg.max_steps if max_steps is None else min(cfg.max_steps, max_steps)
@@ -198,6 +204,8 @@ class Trainer:
         logger.finish()
         if mngr is not None:
             mngr.wait_until_finished()
+        if remote is not None and m.is_main:
+            remote.push_file("metrics.jsonl")
         return last
 
 

@@ -65,9 +65,15 @@ def main(argv=None):
     from midgpt_b200.models.gpt import GPTModel, DictProvider
     from midgpt_b200.ops import get_backend
 
-    if args.ckpt_dir.startswith("gs://"):
-        raise SystemExit("gs:// checkpoints need gcsfs, which is not available in this image")
-    print("Using local filesystem for checkpoint")
+    from midgpt_b200.utils.remote import RemoteDir, is_remote
+    if is_remote(args.ckpt_dir):          # reference: gcsfs when the path starts with gs:// (sample.py:100-108)
+        print(f"Using remote filesystem for checkpoint ({args.ckpt_dir.split('://', 1)[0]}://)")
+        rd = RemoteDir(args.ckpt_dir)
+        rd.pull_file("config.json")
+        rd.pull_latest_step()
+        args.ckpt_dir = rd.local
+    else:
+        print("Using local filesystem for checkpoint")
     with open(os.path.join(args.ckpt_dir, "config.json")) as f:
         config = config_from_json(f.read())
     print(config)
