@@ -44,9 +44,19 @@ def load_tokenizer(data_dir: str):
         stoi, itos = meta["stoi"], meta["itos"]
         return (lambda s: [stoi[c] for c in s]), (lambda l: "".join(itos.get(i, "\ufffd") for i in l))
     print("No LOCAL meta.pkl found, assuming GPT-2 encodings...")
-    import tiktoken
-    enc = tiktoken.get_encoding("gpt2")
-    return (lambda s: enc.encode(s, allowed_special={"<|endoftext|>"})), (lambda l: enc.decode(l))
+    try:
+        import tiktoken
+        enc = tiktoken.get_encoding("gpt2")
+        return (lambda s: enc.encode(s, allowed_special={"<|endoftext|>"})), (lambda l: enc.decode(l))
+    except ImportError:
+        pass
+    try:                                   # same vocabulary through a locally cached HF tokenizer (no network access attempted)
+        from transformers import AutoTokenizer
+        tok = AutoTokenizer.from_pretrained("gpt2", local_files_only=True)
+        return (lambda s: tok.encode(s)), (lambda l: tok.decode(l))
+    except Exception as e:
+        raise SystemExit("GPT-2 BPE needs `tiktoken` (or a locally cached transformers 'gpt2' tokenizer); neither is available: "
+                         f"{type(e).__name__}: {e}")
 
 
 def main(argv=None):
