@@ -108,7 +108,8 @@ def reference_arm():
         why = "jax present but reference not installed under baseline/_ref" if not os.path.isdir(ref) else why
     except Exception:
         pass
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:          # one line per job, also under torchrun
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
     return 0
 
 
