@@ -117,9 +117,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* v_full = bars + 5;        // 2
   uint64_t* v_empty = bars + 7;       // 2
   uint64_t* s_full = bars + 9;        // 2 (one per S buffer)
-  uint64_t* p_full = bars + 11;       // 1 (128 arrivals)
-  uint64_t* pv_done = bars + 12;      // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* p_full = bars + 11;       // 2 (128 arrivals each; one per S/P buffer -- a softmax warp may run a tile ahead of the others, and its
+                                      //    arrival for tile j+1 must not be counted towards tile j: tile j+2 cannot start before p_full(j) completed)
+  uint64_t* pv_done = bars + 13;      // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;          // heavy (late) query tiles first
@@ -131,7 +132,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(p_full, 128); mbar_init(pv_done, 1);
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&p_full[0], 128); mbar_init(&p_full[1], 128); mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -189,7 +190,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_qk(0);
       if (n_kv > 1) issue_qk(1);           // S is double buffered: the next QKᵀ never waits for the softmax
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(p_full, j & 1);          // P_j is in tensor memory (over the S_j columns every thread has already read)
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // P_j is in tensor memory (over the S_j columns every thread has already read)
         tc_fence_after();
         const int st = j & 1;
         mbar_wait(&v_full[st], (j >> 1) & 1);
@@ -310,7 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j & 1]);
     }
     // epilogue: O / l -> bf16 -> global ; lse
     mbar_wait(pv_done, (n_kv - 1) & 1);
