@@ -12,6 +12,9 @@ step, so N = 8 is exactly the reference's global batch of 1024 sequences.  Each 
 step: forward, backward, gradient reduction, global-norm clip, AdamW, bf16 re-gather.  Synthetic tokens,
 random-init weights (no network for datasets/checkpoints).
 
+The same invocation also measures the second half of BASELINE.json's metric, the 124M ``openwebtext`` config
+(reference src/configs/openwebtext.py:4-22) run as FSDP with the same weak-scaling layout, reported under ``"secondary"``.
+
 Two numbers:
   * ``value``  — device-timed (CUDA events, max over ranks) with batches already resident on the GPU;
   * ``e2e``    — the same K steps through the public API (``PinnedBatchLoader`` → ``Trainer.train_step`` →
@@ -49,6 +52,7 @@ def parse():
     p.add_argument("--remat", default="auto", choices=["auto", "block", "none"])
     p.add_argument("--gather-mode", default="auto")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-secondary", action="store_true", help="skip the secondary 124M (openwebtext) measurement")
     p.add_argument("--fp8", action="store_true", help="e4m3 forward GEMMs (separate config; the headline number is bf16)")
     p.add_argument("--fp8-format", default="mx", choices=["mx", "row"])
     p.add_argument("--set", action="append", default=[])
@@ -113,15 +117,10 @@ def reference_arm():
     return 0
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return reference_arm()
-    if args.gpus > 1 and "RANK" not in os.environ:
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
-        return subprocess.call(cmd)
-
+def run_config(args, name: str, steps: int, warmup: int, want_e2e: bool, clocks_on: bool):
+    """Train ``name`` for ``warmup`` + ``steps`` optimizer steps (weak scaling: --seqs-per-gpu sequences per GPU, FSDP over
+    all GPUs of the node) and return the measurements of one config as a dict (rank 0) — the headline config and the
+    secondary 124M config go through exactly the same code."""
     import torch
     import torch.distributed as dist
     from midgpt_b200 import load_config
@@ -129,14 +128,13 @@ def main():
     from midgpt_b200.models.params import flops_per_token
     from midgpt_b200.train import Trainer
     from midgpt_b200.utils import obs
-    sys.path.insert(0, ROOT)
     from launch import apply_overrides
 
-    cfg = load_config(args.config)
+    cfg = load_config(name)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     cfg.batch_size = args.seqs_per_gpu * world
     cfg.g_accum_iters = 1
+    cfg.shard_model = True            # BASELINE.json runs every GPU config as FSDP (the 124M preset itself is pure DP)
     cfg.engine.backend = args.backend
     cfg.engine.comm = args.comm
     cfg.engine.gather_mode = args.gather_mode
@@ -145,12 +143,10 @@ def main():
     cfg.engine.fp8_format = args.fp8_format
     apply_overrides(cfg, args.set)
     T = cfg.model_config.block_size
-    if args.remat == "auto":
-        # full activation stash needs ~70 KB/token for the 1.5 B model; keep it when it fits comfortably in 180 GB
-        cfg.engine.remat = "none"
-    else:
-        cfg.engine.remat = args.remat
+    # full activation stash needs ~70 KB/token for the 1.5 B model; keep it when it fits comfortably in 180 GB
+    cfg.engine.remat = "none" if args.remat == "auto" else args.remat
 
+    torch.cuda.reset_peak_memory_stats()
     tr = Trainer(cfg, device_type="cuda")
     m = tr.mesh
     dev = m.device
@@ -172,77 +168,124 @@ def main():
         return t.item()
 
     # ------------------------------------------------------------------ warm-up (also compiles nothing: no JIT)
-    for i in range(args.warmup):
+    loss = None
+    for i in range(warmup):
         x, y = resident[i % n_resident]
         loss = tr.train_step(x, y)
     sync()
-    loss_w = loss.item() if args.warmup else float("nan")
+    loss_w = loss.item() if warmup else float("nan")
+    tr.engine.measure_comm = True
+    tr.engine.exposed_comm_ms()                         # reset the accounting: only the timed steps count
 
     # ------------------------------------------------------------------ device-timed region
     clocks = ClockSampler(m.local_rank)
-    if m.is_main:
+    if m.is_main and clocks_on:
         clocks.start()
     launches0 = getattr(tr.backend, "launches", 0)
+    comm0 = tr.engine.comm_stats()
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        x, y = resident[(args.warmup + i) % n_resident]
+    for i in range(steps):
+        x, y = resident[(warmup + i) % n_resident]
         loss = tr.train_step(x, y)
     e1.record()
     sync()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = getattr(tr.backend, "launches", 0) - launches0
-    clk = clocks.stop() if m.is_main else {}
-    ms_per_step = ms_total / args.steps
+    comm1 = tr.engine.comm_stats()
+    clk = clocks.stop() if (m.is_main and clocks_on) else {}
+    ms_per_step = ms_total / steps
     tokens_per_step = tr.tokens_per_step
     value = tokens_per_step / (ms_per_step * 1e-3)
     final_loss = loss.item()
 
+    # exposed communication: time the compute stream spent waiting for the comm stream / running the un-overlappable
+    # tail (Σg² all-reduce, AdamW ⊕ all-gather push, barriers), measured with events around those regions, max over ranks
+    comm = {k: comm1[k] - comm0[k] for k in comm1 if isinstance(comm1[k], (int, float))}
+    comm_exposed_ms = max_over_ranks(tr.engine.exposed_comm_ms()) / max(steps, 1) if world > 1 else 0.0
+    tr.engine.measure_comm = False
+
     # ------------------------------------------------------------------ end-to-end region (public API, H2D + D2H every step)
     e2e = None
-    if not args.no_e2e:
+    if want_e2e:
         corpus = synthetic_tokens(max(8 * T * tr.local_seqs, 1 << 22), V, seed=7 + m.rank)
         loader = PinnedBatchLoader(BatchSampler(corpus, T, seed=11 + m.rank), tr.local_seqs, dev)
         x, y = loader.next()
         tr.train_step(x, y).item()                      # one untimed step to prime the loader pipeline
         sync()
         t0 = time.perf_counter()
-        for i in range(args.steps):
+        lv = float("nan")
+        for i in range(steps):
             x, y = loader.next()                        # pinned host -> device copy of this step's batch
             lv = tr.train_step(x, y).item()             # device -> host read of this step's loss
         sync()
         dt = max_over_ranks(time.perf_counter() - t0)
         loader.close()
-        e2e = {"value": tokens_per_step * args.steps / dt, "unit": "tokens/s",
+        e2e = {"value": tokens_per_step * steps / dt, "unit": "tokens/s",
                "h2d_bytes_per_step": loader.h2d_bytes_per_batch * world, "d2h_bytes_per_step": 4 * world,
-               "ms_per_step": dt / args.steps * 1e3, "last_loss": lv}
+               "ms_per_step": dt / steps * 1e3, "last_loss": lv}
 
-    if m.is_main:
-        peak, how = obs.peak_flops_per_gpu()
-        fpt = flops_per_token(cfg.model_config)
-        out = {
-            "metric": "training throughput, 1.5B openwebtext_xl (tokens/s)" if args.config == "openwebtext_xl" else f"training throughput, {args.config} (tokens/s)",
-            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": value / PUBLISHED_TOKENS_PER_S if args.config == "openwebtext_xl" else None,
-            "dtype": "bf16" if not args.fp8 else f"fp8-e4m3 forward GEMMs ({'MX block-scaled' if args.fp8_format == 'mx' else 'row-scaled'}) / bf16 backward", "data": "synthetic tokens, random-init weights",
-            "impl": "ours",
-            "mfu_nominal_2.25PF": value * fpt / (2.25e15 * world),
-            f"mfu_{how}_cublas_peak": value * fpt / (peak * world),
-            "config": {"model": f"{args.config} L{cfg.model_config.n_layer} H{cfg.model_config.n_head} D{cfg.model_config.n_embd} T{T} V{V}",
-                       "global_batch": cfg.batch_size, "seq_len": T,
-                       "parallelism": (f"fsdp{m.shard_size}" if m.shard_size > 1 else "single") + (f"xdp{m.replica_size}" if m.replica_size > 1 else ""),
-                       "micro_batch": tr.micro_bs, "n_micro": tr.n_micro, "remat": cfg.engine.remat, "backend": tr.backend.name,
-                       "comm": tr.engine.comm, "gather_mode": tr.engine.gather_mode,
-                       "l2": "no L2 flush needed: per-step working set (2.8 GB bf16 weights + GBs of activations, 4 rotating batches) >> 126 MB L2"},
-            "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons"),
-                       "power_w_max": clk.get("power_w_max")},
-            "e2e": e2e, "gpu_launches": launches, "loss_after_warmup": loss_w, "final_loss": final_loss,
-            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
-        }
+    peak, how = obs.peak_flops_per_gpu()
+    fpt = flops_per_token(cfg.model_config)
+    mc = cfg.model_config
+    out = {
+        "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+        "mfu_nominal_2.25PF": value * fpt / (2.25e15 * world),
+        f"mfu_{how}_cublas_peak": value * fpt / (peak * world),
+        "config": {"model": f"{name} L{mc.n_layer} H{mc.n_head} D{mc.n_embd} T{T} V{V}",
+                   "global_batch": cfg.batch_size, "seq_len": T,
+                   "parallelism": (f"fsdp{m.shard_size}" if m.shard_size > 1 else "single") + (f"xdp{m.replica_size}" if m.replica_size > 1 else ""),
+                   "micro_batch": tr.micro_bs, "n_micro": tr.n_micro, "remat": cfg.engine.remat, "backend": tr.backend.name,
+                   "comm": tr.engine.comm, "gather_mode": tr.engine.gather_mode,
+                   "l2": "no L2 flush needed: per-step working set (GBs of bf16 weights + activations, 4 rotating batches) >> 126 MB L2"},
+        "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons"),
+                   "power_w_max": clk.get("power_w_max")},
+        "e2e": e2e, "gpu_launches": launches, "loss_after_warmup": loss_w, "final_loss": final_loss,
+        "comm_exposed_ms": comm_exposed_ms, "comm_kernel_launches": comm,
+        "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
+    }
+    # free everything before the next config: symmetric arenas, pinned buffers, activations
+    del tr, resident
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    rank = int(os.environ.get("RANK", "0"))
+
+    head = run_config(args, args.config, args.steps, args.warmup, not args.no_e2e, True)
+    secondary = {}
+    if args.config == "openwebtext_xl" and not args.no_secondary and not args.fp8:
+        # the other half of BASELINE.json's metric ("124M & 1.5B"): reference src/configs/openwebtext.py, as FSDP
+        sec = run_config(args, "openwebtext", max(args.steps, 6), max(args.warmup, 3), not args.no_e2e, False)
+        secondary["openwebtext_124M"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "mfu_nominal_2.25PF", "e2e", "config",
+                                                           "steps", "warmup", "gpu_launches", "comm_exposed_ms", "peak_mem_GB", "final_loss")}
+    if rank == 0:
+        fp8 = args.fp8
+        out = {"metric": "training throughput, 1.5B openwebtext_xl (tokens/s)" if args.config == "openwebtext_xl" else f"training throughput, {args.config} (tokens/s)"}
+        out.update(head)
+        out.update({
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": head["value"] / PUBLISHED_TOKENS_PER_S if args.config == "openwebtext_xl" else None,
+            "dtype": "bf16" if not fp8 else f"fp8-e4m3 GEMMs ({'MX block-scaled' if args.fp8_format == 'mx' else 'row-scaled'})",
+            "data": "synthetic tokens, random-init weights", "impl": "ours", "secondary": secondary,
+        })
         print(json.dumps(out))
-    if world > 1:
+    if world > 1 and dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()
     return 0

@@ -1,11 +1,17 @@
 """Tokenise OpenWebText into ``train.bin`` / ``val.bin`` (flat uint16 GPT-2 BPE ids, EOT after each doc).
 
 Output contract = reference data/openwebtext/prepare.py:41-73: ``encode_ordinary`` + EOT 50256 appended,
-0.05 % validation split with seed 2357, uint16 memmaps (~9.04 B train / ~4.4 M val tokens).
-Differences: documents can also come from local ``*.txt``/``*.jsonl`` shards (``--source``; no network on
-the training hosts — HF ``datasets`` is used only when available), tokenisation is streamed through a
-process pool straight into the output memmap (two passes: count, then write) instead of materialising a
-tokenised HF dataset, and ``--synthetic N`` writes N Zipf-distributed tokens for benchmarking.
+0.05 % validation split with seed 2357, uint16 files (~9.04 B train / ~4.4 M val tokens).
+
+* With HF ``datasets`` installed (the reference's path, prepare.py:21-25) the split is *the reference's split*:
+  ``dataset["train"].train_test_split(test_size=0.0005, seed=2357, shuffle=True)`` — same documents in ``val.bin``.
+* Without it (no network on the training hosts) documents come from local ``*.txt`` / ``*.jsonl`` shards (``--source``) and
+  the split is a seeded (2357) permutation of the document indices — same fraction, not the same documents.
+* Either way documents are **streamed**: a bounded window of documents is tokenised by a process pool and the ids are
+  appended to the output file in document order, so peak RAM is O(window), not O(corpus).  (The reference sizes a memmap
+  from a tokenised Arrow dataset and fills it in 1024 write-batches, prepare.py:58-73; appending produces the same bytes
+  without knowing the total in advance, so no counting pass is needed.)
+* ``--synthetic N`` writes N Zipf-distributed tokens for benchmarking.
 """
 import argparse
 import glob
@@ -30,25 +36,42 @@ def iter_local_docs(source):
                 yield f.read()
 
 
-def _encode(text):
-    import tiktoken
-    enc = tiktoken.get_encoding("gpt2")
-    ids = enc.encode_ordinary(text)
+def _encode(text, tokenizer="gpt2"):
+    if tokenizer == "bytes":            # offline / test tokenizer: UTF-8 bytes (the GPT-2 BPE files need a download)
+        ids = list(text.encode("utf-8"))
+    else:
+        import tiktoken
+        enc = tiktoken.get_encoding("gpt2")
+        ids = enc.encode_ordinary(text)
     ids.append(EOT)
     return np.asarray(ids, dtype=np.uint16)
 
 
-def write_split(docs, path, workers):
+def stream_tokenise(docs, files, route, workers, window=4096, tokenizer="gpt2"):
+    """Tokenise ``docs`` (any iterable of strings, consumed lazily) and append every document's ids to
+    ``files[route(i)]`` in document order.  At most ``window`` documents / token arrays are alive at any time."""
+    from collections import deque
+    totals = {k: 0 for k in files}
+    pending = deque()
+
+    def drain_one():
+        k, fut = pending.popleft()
+        a = fut.result()
+        a.tofile(files[k])
+        totals[k] += len(a)
+
     with ProcessPoolExecutor(workers) as ex:
-        arrays = list(ex.map(_encode, docs, chunksize=64))
-    total = int(sum(len(a) for a in arrays))
-    out = np.memmap(path, dtype=np.uint16, mode="w+", shape=(total,))
-    pos = 0
-    for a in arrays:
-        out[pos:pos + len(a)] = a
-        pos += len(a)
-    out.flush()
-    print(f"{path}: {total:,} tokens")
+        for i, text in enumerate(docs):
+            pending.append((route(i), ex.submit(_encode, text, tokenizer)))
+            if len(pending) >= window:
+                drain_one()
+        while pending:
+            drain_one()
+    return totals
+
+
+def count_docs(source):
+    return sum(1 for _ in iter_local_docs(source))
 
 
 def main():
@@ -57,6 +80,8 @@ def main():
     ap.add_argument("--out", default=HERE)
     ap.add_argument("--workers", type=int, default=max(1, (os.cpu_count() or 2) // 2))
     ap.add_argument("--synthetic", type=int, default=0, help="write this many synthetic tokens instead")
+    ap.add_argument("--tokenizer", default="gpt2", choices=["gpt2", "bytes"])
+    ap.add_argument("--window", type=int, default=4096, help="documents in flight (bounds peak RAM)")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     if args.synthetic:
@@ -66,17 +91,26 @@ def main():
         synthetic_tokens(args.synthetic, 50257, seed=1).tofile(os.path.join(args.out, "train.bin"))
         synthetic_tokens(max(args.synthetic // 2000, 4096), 50257, seed=2).tofile(os.path.join(args.out, "val.bin"))
         return
+    train_path, val_path = os.path.join(args.out, "train.bin"), os.path.join(args.out, "val.bin")
     if args.source:
-        docs = list(iter_local_docs(args.source))
+        n_docs = count_docs(args.source)                      # cheap pass over the shards: no tokenisation, nothing kept
+        rng = np.random.default_rng(2357)
+        n_val = max(1, int(round(n_docs * 0.0005)))
+        val_idx = set(rng.permutation(n_docs)[:n_val].tolist())
+        with open(train_path, "wb") as ft, open(val_path, "wb") as fv:
+            totals = stream_tokenise(iter_local_docs(args.source), {"train": ft, "val": fv},
+                                     lambda i: "val" if i in val_idx else "train", args.workers, args.window, args.tokenizer)
     else:
         from datasets import load_dataset
-        docs = load_dataset("openwebtext", num_proc=args.workers)["train"]["text"]
-    rng = np.random.default_rng(2357)
-    perm = rng.permutation(len(docs))
-    n_val = max(1, int(round(len(docs) * 0.0005)))
-    val_idx = set(perm[:n_val].tolist())
-    write_split([d for i, d in enumerate(docs) if i in val_idx], os.path.join(args.out, "val.bin"), args.workers)
-    write_split([d for i, d in enumerate(docs) if i not in val_idx], os.path.join(args.out, "train.bin"), args.workers)
+        dataset = load_dataset("openwebtext", num_proc=args.workers)
+        split = dataset["train"].train_test_split(test_size=0.0005, seed=2357, shuffle=True)   # the reference's split
+        totals = {}
+        for name, path, dset in (("train", train_path, split["train"]), ("val", val_path, split["test"])):
+            with open(path, "wb") as f:
+                totals.update(stream_tokenise((ex["text"] for ex in dset), {name: f}, lambda i, name=name: name,
+                                              args.workers, args.window, args.tokenizer))
+    for k, v in totals.items():
+        print(f"{k}.bin: {v:,} tokens")
 
 
 if __name__ == "__main__":

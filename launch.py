@@ -41,6 +41,22 @@ def parse_args(argv=None):
     return p.parse_args(argv)
 
 
+def strip_nproc(argv):
+    """Child argv for the self-spawn: drop ``--nproc N`` (two tokens) and ``--nproc=N`` (one token)."""
+    out, skip = [], False
+    for a in argv:
+        if skip:
+            skip = False
+            continue
+        if a == "--nproc":
+            skip = True
+            continue
+        if a.startswith("--nproc="):
+            continue
+        out.append(a)
+    return out
+
+
 def apply_overrides(config, pairs):
     for kv in pairs:
         k, v = kv.split("=", 1)
@@ -68,7 +84,7 @@ def main(argv=None):
         import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.nproc}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
-               os.path.abspath(__file__)] + [a for a in (argv or sys.argv[1:]) if not a.startswith("--nproc")]
+               os.path.abspath(__file__)] + strip_nproc(list(argv or sys.argv[1:]))
         if not args.rundir and not args.debug:
             cmd += ["--rundir", os.path.join("outputs", datetime.now().strftime("%Y-%m-%d-%H-%M-%S"))]
         raise SystemExit(subprocess.call(cmd))

@@ -5,21 +5,22 @@ AsyncCheckpointer(PyTreeCheckpointHandler()), max_to_keep=1, save_interval_steps
 ``mngr.save(itr, (model_leaves, opt_leaves))`` is *called* every step and the manager skips steps off
 the interval; resume = ``latest_step()`` → ``restore`` → ``first_step = latest + 1``.
 
-On-disk layout ([lib]-inferred):
+On-disk layout (schema provenance in ``layout.py``):
 
     <rundir>/<step>/default/
-        _METADATA            json: tree metadata (key → shape/dtype/kind)
-        checkpoint           msgpack aggregate: scalar leaves inline, arrays as "PLACEHOLDER://<key>"
+        _METADATA            json: Orbax ``tree_metadata`` (one entry per leaf: key tuple, key types, value type)
+        checkpoint           msgpack aggregate of the nested ``(model_leaves, opt_leaves)`` tree: scalar leaves inline,
+                             array leaves as "PLACEHOLDER://<key>"
         0.0/ 0.5/ … 1.16/    one Zarr-v2 array per array leaf (see zarrio.py)
-    <rundir>/<step>/extra.json   (ours: sampler RNG state, world size — the reference loses these)
+    <rundir>/<step>/extra.json, extra_rank<r>.json   (ours: per-rank sampler RNG state, world size — the reference loses these)
 
-Distributed write: for every FSDP unit the fp32 master / m / v shards are all-gathered (a
-collective every rank joins), and rank ``unit % world`` writes that unit's chunks — one chunk per
-layer for the stacked block leaves — so file IO is spread over all ranks.  Device→host copy is
-synchronous, file writing happens on a background thread (async like Orbax's AsyncCheckpointer),
-the step directory is committed by an atomic rename once every rank's marker file exists.
-Restore maps chunk files with ``np.memmap`` and copies only the byte ranges of the local shard, so
-a run may resume on a different world size.
+Distributed write — **no collective moves tensor data**: every rank copies only its own fp32 master / m / v shards to
+pinned host memory on a side stream (the next optimizer step waits for that copy on the device; the host does not), and a
+background thread writes exactly the byte ranges the rank owns into the (uncompressed, raw little-endian) Zarr chunk files
+with ``pwrite`` — a chunk is one layer of one leaf, and a rank's flat shard covers a contiguous byte range of a few of
+them.  The step directory is committed by an atomic rename once every rank's marker file exists.  Restore maps chunk files
+with ``np.memmap`` and copies only the byte ranges of the local shard, so a run may resume on a different world size.
+``save()`` returns after *enqueueing* the device→host copies; its stall is reported as ``last_save_stall_ms``.
 """
 from __future__ import annotations
 
@@ -77,9 +78,18 @@ class CheckpointManager:
         return step % self.interval == 0
 
     # ------------------------------------------------------------------ save
+    def _host_buffer(self, n: int, cuda: bool) -> torch.Tensor:
+        """One reusable (pinned, on CUDA) fp32 staging buffer; the previous save's writer thread has been joined."""
+        buf = getattr(self, "_hbuf", None)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(n, dtype=torch.float32, pin_memory=cuda)
+            self._hbuf = buf
+        return buf[:n]
+
     def save(self, step: int, engine, extra: dict | None = None, force: bool = False) -> bool:
         if not (force or self.should_save(step)):
             return False
+        t_begin = time.perf_counter()
         self.wait_until_finished()
         mesh = engine.mesh
         rank, world = mesh.rank, mesh.world
@@ -96,49 +106,74 @@ class CheckpointManager:
             if os.path.exists(tmp):
                 shutil.rmtree(tmp)
             os.makedirs(item)
-            meta_tree, agg = {}, {}
+            scalars: tp.Dict[str, tp.Any] = {}
+            for i, (kind, src) in enumerate(layout.MODEL_LEAVES):
+                if kind == "scalar":
+                    scalars[layout.model_key(i)] = src(cfg)
+            for key, which, name in layout.opt_layout():
+                if which == "count":
+                    scalars[key] = int(engine.count)
             for (which, name), key in keys.items():
                 shp = shapes[name]
                 chunks = shp if name in ("wte", "lm_head") else (1,) + shp[1:]
                 zarrio.write_zarray_meta(os.path.join(item, key), shp, chunks, "float32")
-                meta_tree[key] = {"kind": "array", "shape": list(shp), "dtype": "float32", "which": which, "leaf": name}
-                agg[key] = f"PLACEHOLDER://{key}"
-            for i, (kind, src) in enumerate(layout.MODEL_LEAVES):
-                if kind == "scalar":
-                    agg[layout.model_key(i)] = src(cfg)
-                    meta_tree[layout.model_key(i)] = {"kind": "scalar"}
-            for key, which, name in layout.opt_layout():
-                if which == "count":
-                    agg[key] = int(engine.count)
-                    meta_tree[key] = {"kind": "scalar", "leaf": f"{name}_count"}
             with open(os.path.join(item, "_METADATA"), "w") as f:
-                json.dump({"tree_metadata": meta_tree, "format": "midgpt_b200-orbax-zarr2", "version": 1}, f)
+                json.dump(layout.tree_metadata(set(keys.values()), scalars), f)
             with open(os.path.join(item, "checkpoint"), "wb") as f:
-                f.write(msgpack.packb(agg))
+                f.write(msgpack.packb(layout.aggregate_tree(set(keys.values()), scalars)))
             with open(os.path.join(tmp, "extra.json"), "w") as f:
                 json.dump({"extra": extra or {}, "world": world, "count": int(engine.count), "step": step}, f)
         if world > 1:
-            torch.distributed.barrier()
-        # synchronous part: gather + D2H
-        jobs: tp.List[tp.Tuple[str, tp.Tuple[int, ...], np.ndarray]] = []
-        for i, u in enumerate(engine.units):
-            for which in ("master", "exp_avg", "exp_avg_sq"):
-                full = engine.full_unit_state(i, which)            # collective
-                if i % world != rank:
-                    continue
-                for pname, t in ((p.name, full[f"{u.spec.name}.{p.name}"]) for p in u.spec.params):
-                    arr = t.detach().to("cpu", torch.float32).numpy().copy()
-                    if u.spec.name in ("embed", "head"):
-                        jobs.append((os.path.join(item, keys[(which, pname)]), (0,) * arr.ndim, arr))
-                    else:
-                        l = int(u.spec.name.split(".")[1])
-                        jobs.append((os.path.join(item, keys[(which, pname)]), (l,) + (0,) * arr.ndim, arr[None]))
-                del full
+            torch.distributed.barrier()          # the directory skeleton exists before anybody writes into it
+        with open(os.path.join(tmp, f"extra_rank{rank}.json"), "w") as f:
+            json.dump({"extra": extra or {}, "world": world}, f)
+
+        # ---- device -> pinned host, this rank's shards only, on a side stream; the optimizer waits for it, the host does not
+        sr = engine.sr
+        cuda = engine.cuda
+        total = 3 * sum(u.shard for u in engine.units)
+        host = self._host_buffer(total, cuda)
+        jobs: tp.List[tp.Tuple[str, tp.Tuple[int, ...], int, int, int]] = []   # (leaf dir, chunk idx, byte offset in chunk, host off, n)
+        if cuda:
+            if getattr(self, "_stream", None) is None:
+                self._stream = torch.cuda.Stream(engine.device)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            self._stream.wait_event(ready)
+        off = 0
+        for u in engine.units:
+            lo, hi = sr * u.shard, (sr + 1) * u.shard
+            layer = None if u.spec.name in ("embed", "head") else int(u.spec.name.split(".")[1])
+            for which, src in (("master", u.master), ("exp_avg", u.exp_avg), ("exp_avg_sq", u.exp_avg_sq)):
+                dst = host[off:off + u.shard]
+                if cuda:
+                    with torch.cuda.stream(self._stream):
+                        dst.copy_(src if src.dtype == torch.float32 else src.float(), non_blocking=True)
+                else:
+                    dst.copy_(src.detach().float())
+                for p in u.spec.params:
+                    a, b = max(lo, p.offset), min(hi, p.offset + p.numel)
+                    if a >= b:
+                        continue
+                    nd = len(shapes[p.name])
+                    idx = (0,) * nd if layer is None else (layer,) + (0,) * (nd - 1)
+                    jobs.append((os.path.join(item, keys[(which, p.name)]), idx, (a - p.offset) * 4, off + (a - lo), b - a))
+                off += u.shard
+        done = None
+        if cuda:
+            done = torch.cuda.Event()
+            done.record(self._stream)
+            engine.defer_state_update_until(done)       # the next AdamW sweep must not overwrite shards still being copied
+        chunk_bytes = {name: 4 * int(np.prod(shapes[name] if name in ("wte", "lm_head") else shapes[name][1:])) for name in shapes}
+        key_to_name = {key: name for (which, name), key in keys.items()}
 
         def commit():
             try:
-                for path, idx, arr in jobs:
-                    zarrio.write_chunk(path, idx, arr)
+                if done is not None:
+                    done.synchronize()
+                hv = host.numpy()
+                for path, idx, boff, hoff, n in jobs:
+                    zarrio.write_chunk_range(path, idx, boff, hv[hoff:hoff + n], chunk_bytes[key_to_name[os.path.basename(path)]])
                 with open(os.path.join(tmp, f".done_rank{rank}"), "w") as f:
                     f.write("ok")
                 if rank == 0:
@@ -165,6 +200,7 @@ class CheckpointManager:
         else:
             commit()
             self._raise()
+        self.last_save_stall_ms = (time.perf_counter() - t_begin) * 1e3
         return True
 
     def _prune(self) -> None:
@@ -211,11 +247,22 @@ class CheckpointManager:
             for which in ("master", "exp_avg", "exp_avg_sq"):
                 engine.load_unit_shard_np(i, which, lambda pname, which=which, l=l: chunk(which, pname, l))
         count_key = [k for k, w, n in layout.opt_layout() if w == "count"][0]
-        engine.count = int(agg[count_key])
-        extra_path = os.path.join(self.dir, str(step), "extra.json")
+        engine.count = int(layout.aggregate_lookup(agg, count_key))
+        # per-rank extra (sampler RNG) when the world size is unchanged, rank 0's otherwise (flagged, so the caller can
+        # de-correlate the streams instead of replaying rank 0's on every rank)
+        sdir = os.path.join(self.dir, str(step))
+        mine = os.path.join(sdir, f"extra_rank{engine.mesh.rank}.json")
+        if os.path.exists(mine):
+            with open(mine) as f:
+                d = json.load(f)
+            if d.get("world") == engine.mesh.world:
+                return d.get("extra", {})
+        extra_path = os.path.join(sdir, "extra.json")
         if os.path.exists(extra_path):
             with open(extra_path) as f:
-                return json.load(f).get("extra", {})
+                ex = dict(json.load(f).get("extra", {}))
+            ex["_from_other_rank"] = True
+            return ex
         return {}
 
     def restore_full_params(self, step: int, cfg, which: str = "master") -> tp.Dict[str, torch.Tensor]:

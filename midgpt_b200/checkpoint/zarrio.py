@@ -36,6 +36,23 @@ def write_chunk(path: str, idx: tp.Sequence[int], data: np.ndarray) -> None:
     os.replace(tmp, os.path.join(path, chunk_name(idx)))
 
 
+def write_chunk_range(path: str, idx: tp.Sequence[int], byte_offset: int, data: np.ndarray, chunk_bytes: int) -> None:
+    """Write ``data`` into the byte range [byte_offset, +nbytes) of one (raw, uncompressed) chunk file.  Several ranks write
+    disjoint ranges of the same chunk concurrently: the file is created if missing and sized to ``chunk_bytes`` (ftruncate to
+    the same size is idempotent and never discards bytes another rank already wrote)."""
+    os.makedirs(path, exist_ok=True)
+    fd = os.open(os.path.join(path, chunk_name(idx)), os.O_RDWR | os.O_CREAT, 0o644)
+    try:
+        if os.fstat(fd).st_size < chunk_bytes:
+            os.ftruncate(fd, chunk_bytes)
+        buf = memoryview(np.ascontiguousarray(data)).cast("B")
+        done = 0
+        while done < len(buf):
+            done += os.pwrite(fd, buf[done:], byte_offset + done)
+    finally:
+        os.close(fd)
+
+
 def read_meta(path: str) -> dict:
     with open(os.path.join(path, ".zarray")) as f:
         return json.load(f)

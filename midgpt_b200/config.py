@@ -44,7 +44,6 @@ class EngineConfig:
     prefetch_depth: int = 2        # units gathered ahead of the consumer when gather_mode == "layer"
     fp8: bool = False              # forward GEMMs of the blocks in e4m3 on the fp8 tensor cores; backward stays bf16
     fp8_format: str = "mx"         # "mx": OCP MX block scaling (UE8M0 per 32 elements, tcgen05 block_scale) | "row": one fp32 scale per row
-    cuda_graphs: bool = False
     seed: int = 0
     log_every: int = 20
     ckpt_async: bool = True

@@ -7,8 +7,9 @@ copied into host RAM, each *process* keeps a contiguous ``1/n_proc`` slice, and 
 
 * one process per GPU ⇒ 8 processes per node; the file stays a shared read-only memmap (page
   cache is shared) instead of 8 private RAM copies;
-* the sampler owns a seeded ``numpy.random.Generator`` whose state is saved in checkpoints, so a
-  resumed run continues the same sample stream (the reference restarts it, SURVEY.md §5.3);
+* the sampler owns a seeded ``numpy.random.Generator``; the prefetching loader snapshots its state together with
+  every batch it produces, and checkpoints store — per rank — the state that follows the batch the trainer actually
+  *consumed*, so a resumed run continues the same sample stream exactly (the reference restarts it, SURVEY.md §5.3);
 * batches are assembled straight into **pinned** host buffers by a background thread (or the
   native C++ gatherer in ``csrc/dataloader.cpp`` when built) and copied H2D on a side stream (X9).
 * a synthetic corpus of the right vocabulary/length stands in when no dataset is on disk
@@ -128,6 +129,8 @@ class PinnedBatchLoader:
         for i in range(len(self._bufs)):
             self._free.put(i)
         self._inflight: tp.List[tp.Tuple[int, tp.Any]] = []
+        self._state_after: tp.List[dict | None] = [None] * len(self._bufs)
+        self._consumed_state = sampler.state_dict()
         self._background = background
         self._stop = False
         if background:
@@ -137,6 +140,12 @@ class PinnedBatchLoader:
     def _fill(self, i: int) -> None:
         x, y = self._bufs[i]
         self.sampler.sample_into(x.numpy(), y.numpy())
+        self._state_after[i] = self.sampler.state_dict()      # RNG state that follows this batch
+
+    def state_dict(self) -> dict:
+        """Sampler state to checkpoint: the one following the last batch handed out by ``next()`` — NOT the live state of
+        the sampler, which the prefetch thread has already advanced by up to ``prefetch + 1`` batches."""
+        return self._consumed_state
 
     def _work(self) -> None:
         while not self._stop:
@@ -162,6 +171,7 @@ class PinnedBatchLoader:
             i = self._free.get()
             self._fill(i)
         hx, hy = self._bufs[i]
+        self._consumed_state = self._state_after[i]
         if not self.cuda:
             out = (hx.clone(), hy.clone())
             self._free.put(i)

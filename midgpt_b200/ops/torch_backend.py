@@ -5,7 +5,7 @@ This backend serves three purposes:
   2. the "library baseline" on GPU (cuBLAS GEMMs + aten flash attention) that the hand-written
      sm_100a backend in ``b200_backend.py`` must beat;
   3. an executable specification of each primitive's backward, validated against autograd of
-     ``models/oracle.py`` in ``tests/test_backend_torch.py``.
+     ``models/oracle.py`` in ``tests/test_model_backward.py``.
 
 All activations are token-major 2-D tensors ``[M = B·T, features]``.
 Op ↔ SURVEY.md §2.4 mapping: embed K1, rmsnorm K2, linear K3/K7/K8/K9, qkln_rope K4+K5,

@@ -95,11 +95,15 @@ def make_mesh(shard_model: bool, device_type: str | None = None, max_shard: int 
 # Collective wrappers: NCCL fast paths, gloo fall-backs (gloo has no reduce_scatter)
 # ------------------------------------------------------------------------------------------------
 
+COLLECTIVE_CALLS = {"n": 0}      # library collectives issued through this module (bench.py reports the count)
+
+
 def all_gather_flat(out_full: torch.Tensor, in_shard: torch.Tensor, group, backend: str) -> None:
     if group is None:
         if out_full.data_ptr() != in_shard.data_ptr():
             out_full[: in_shard.numel()].copy_(in_shard)
         return
+    COLLECTIVE_CALLS["n"] += 1
     if backend == "nccl":
         dist.all_gather_into_tensor(out_full, in_shard, group=group)
     else:
@@ -115,6 +119,7 @@ def reduce_scatter_avg(out_shard: torch.Tensor, in_full: torch.Tensor, group, ba
             out_shard.copy_(in_full[: out_shard.numel()])
         return
     n = dist.get_world_size(group)
+    COLLECTIVE_CALLS["n"] += 1
     if backend == "nccl":
         dist.reduce_scatter_tensor(out_shard, in_full, op=dist.ReduceOp.AVG, group=group)
     else:
@@ -126,6 +131,7 @@ def reduce_scatter_avg(out_shard: torch.Tensor, in_full: torch.Tensor, group, ba
 def all_reduce_avg(t: torch.Tensor, group, backend: str) -> None:
     if group is None:
         return
+    COLLECTIVE_CALLS["n"] += 1
     if backend == "nccl":
         dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
     else:

@@ -100,6 +100,7 @@ class FSDPEngine:
         self._need_gather = True
         self._micro_is_last = True
         self._pending_reduce: tp.List[int] = []
+        self._exposed_pairs: tp.List[tp.Tuple[tp.Any, tp.Any]] = []
         self.last_grad_norm: torch.Tensor | None = None
         if self.comm == "fused" and self.S > 1:
             from .fused import FusedComm
@@ -235,6 +236,10 @@ class FSDPEngine:
             self._pool_last_use[u.pool_slot] = ev
         self._pool_free.append(u.pool_slot)
         u.lp_full, u.pool_slot, u.gathered_event = None, -1, None
+        if hasattr(self.be, "notify_weights_updated"):
+            # the pool slot (same data_ptr, same shapes) will hold another unit's weights next: cached e4m3 copies keyed on
+            # the pointer would silently be another layer's weights
+            self.be.notify_weights_updated()
         # after the last forward unit the schedule turns around
         if unit == len(self.units) - 1:
             self._direction = -1
@@ -284,15 +289,58 @@ class FSDPEngine:
     def set_micro(self, is_last: bool) -> None:
         self._micro_is_last = is_last
 
+    _state_busy_event = None
+
+    def defer_state_update_until(self, event) -> None:
+        """The fp32 master / m / v shards are being read asynchronously (checkpoint D2H on a side stream): the next
+        optimizer sweep waits for ``event`` on the device before it overwrites them."""
+        self._state_busy_event = event
+
+    # ------------------------------------------------------------------ communication accounting (bench.py)
+    measure_comm = False
+
+    def _mark(self):
+        """Event on the current stream when exposed-communication accounting is on (bench.py), else None."""
+        if not (self.measure_comm and self.cuda):
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def _exposed(self, ev0) -> None:
+        if ev0 is not None:
+            self._exposed_pairs.append((ev0, self._mark()))
+
+    def exposed_comm_ms(self) -> float:
+        """Milliseconds the COMPUTE stream spent on communication that nothing overlapped since the last call: waiting for
+        the comm stream's reduce-scatters, the device barriers, the Σg² all-reduce.  (The AdamW ⊕ all-gather push is not
+        counted: at one GPU the same sweep runs without the push.)  Call after a synchronize."""
+        tot = 0.0
+        for a, b in self._exposed_pairs:
+            tot += a.elapsed_time(b)
+        self._exposed_pairs = []
+        return tot
+
+    def comm_stats(self) -> tp.Dict[str, int]:
+        st = {"nccl_collectives": D.COLLECTIVE_CALLS["n"]}
+        if self.fused is not None:
+            st.update(self.fused.stats)
+        return st
+
     def optimizer_step(self) -> torch.Tensor:
         """Clip → Adam → independent WD → schedule → apply, on the local shards.  Returns ‖g‖ (device scalar)."""
         be = self.be
         if self.cuda:
             cur = torch.cuda.current_stream()
+            if self._state_busy_event is not None:
+                cur.wait_event(self._state_busy_event)
+                self._state_busy_event = None
+            ev0 = self._mark()
             for u in self.units:
                 if u.reduced_event is not None:
                     cur.wait_event(u.reduced_event)
                     u.reduced_event = None
+            self._exposed(ev0)
         if self.fused is not None:
             gnorm = self.fused.optimizer_step()          # RS already pulled per unit; AdamW ⊕ all-gather push
         else:

@@ -98,6 +98,7 @@ class FusedComm:
             self._scratch_flags = torch.zeros(8, dtype=torch.int32, device=dev)     # stand-alone pulls are ordered by the stream
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._pushed = False
+        self.stats = {"xrank_barrier": 0, "rs_sumsq": 0, "adamw_allgather": 0, "ag_pull": 0, "gemm_ag": 0}
         self._barrier()          # every rank has zeroed / initialised its arenas
         if mesh.is_main:
             print(f"[fused-comm] symmetric arenas: grad {total * 4 / 2**30:.2f} GB fp32, weights {total * 2 / 2**30:.2f} GB bf16, "
@@ -107,12 +108,14 @@ class FusedComm:
     def _barrier(self) -> None:
         self.epoch += 1
         self.ext.xrank_barrier(self.pad_ptrs, self.rank, 0, self.epoch)
+        self.stats["xrank_barrier"] += 1
 
     def all_gather(self, u) -> None:
         """step mode: only the very first gather (initial weights) moves data; afterwards AdamW pushes keep lp_arena current.
         layer mode: stand-alone NVLink pull (used where no K-major GEMM is the first consumer, e.g. the embedding)."""
         if self.layer_mode:
             self.ext.ag_pull(self._peer_shard_ptrs(u), u.lp_full, u.shard, self.rank, self._scratch_flags, AG_CTAS)
+            self.stats["ag_pull"] += 1
             return
         if self._pushed:
             return
@@ -138,15 +141,27 @@ class FusedComm:
         self._barrier()                                   # every rank finished accumulating this unit
         off = self.offsets[i] + self.rank * u.shard
         self.ext.rs_sumsq(self.grad_ptrs, self.mc_grad, u.grad_shard, self.sumsq, off, self.rank)
+        self.stats["rs_sumsq"] += 1
 
     def optimizer_step(self) -> torch.Tensor:
         """Runs on the engine's compute stream after all reduce events have been waited on."""
         e = self.e
+        ev0 = e._mark()
         self._barrier()                                   # all pulls everywhere are done -> accumulators reusable
+        e._exposed(ev0)
         self.grad_arena.zero_()
-        total = self.sumsq.clone()
+        if e.mesh.replica_size > 1:
+            # HSDP: rs_sumsq accumulated Σg² of the *intra-node* mean, before the replica all-reduce changed grad_shard;
+            # every replica group would otherwise clip with its own norm and the replicas' weights would drift apart.
+            total = torch.zeros(1, dtype=torch.float32, device=e.device)
+            for u in e.units:
+                self.ext.sumsq_accumulate(u.grad_shard, total)
+        else:
+            total = self.sumsq.clone()
         self.sumsq.zero_()
+        ev0 = e._mark()
         dist.all_reduce(total, group=e.mesh.shard_group)   # 4 bytes
+        e._exposed(ev0)
         clip, gnorm = clip_factor_from_sumsq(total[0])
         sc = step_scalars(e.count, e.cfg)
         clip1 = clip.reshape(1).float()
@@ -158,6 +173,9 @@ class FusedComm:
             off = self.offsets[i] + self.rank * u.shard
             self.ext.adamw_allgather(u.master, u.exp_avg, u.exp_avg_sq, u.grad_shard, self.lp_ptrs, self.mc_lp, off, clip1,
                                      sc.lr, sc.b1, sc.b2, sc.eps, sc.wd_over_lr_peak, sc.bc1, sc.bc2)
+            self.stats["adamw_allgather"] += 1
+        ev0 = e._mark()
         self._barrier()                                   # every rank's pushes have landed everywhere
+        e._exposed(ev0)
         self._pushed = True
         return gnorm

@@ -31,7 +31,10 @@ def auto_micro_batch(cfg: ExperimentConfig, local_seqs: int, device: torch.devic
     """Largest divisor of ``local_seqs`` whose token count stays ≤ a target that keeps GEMMs large
     but activations modest (32 K tokens on GPU, everything on CPU)."""
     if cfg.engine.micro_batch_size > 0:
-        return min(cfg.engine.micro_batch_size, local_seqs)
+        mb = min(cfg.engine.micro_batch_size, local_seqs)
+        while local_seqs % mb:          # a remainder would silently drop sequences and mis-scale loss / gradients
+            mb -= 1
+        return mb
     if device.type != "cuda":
         return local_seqs
     target = max(1, 32768 // cfg.model_config.block_size)
@@ -124,6 +127,9 @@ class Trainer:
         train = split_array_by_idx(train, m.rank, m.world) if len(train) > 2 * m.world * (self.T + 1) else train
         val = split_array_by_idx(val, m.rank, m.world) if len(val) > 2 * m.world * (self.T + 1) else val
         seed = cfg.engine.seed
+        # the training stream has its own generator; evaluate() on the training split uses a third sampler so that it
+        # neither races with the prefetch thread nor perturbs the (checkpointed) training stream
+        self.train_eval_sampler = BatchSampler(train, self.T, seed=seed * 1000 + 250 + m.rank)
         return (BatchSampler(train, self.T, seed=seed * 1000 + m.rank),
                 BatchSampler(val, self.T, seed=seed * 1000 + 500 + m.rank))
 
@@ -152,6 +158,9 @@ class Trainer:
             first_step = mngr.latest_step() + 1
             if extra and "sampler" in extra:
                 train_s.load_state_dict(extra["sampler"])
+                if extra.get("_from_other_rank") and m.rank > 0:
+                    # world size changed since the save: only rank 0's stream is known; give every rank its own jump of it
+                    train_s.rng = type(train_s.rng)(train_s.rng.bit_generator.jumped(m.rank))
             if m.is_main:
                 print(f"[ckpt] resumed from step {first_step - 1}")
         logger = obs.MetricLogger(local_rundir or None, cfg.reference_dict(), enabled=m.is_main,
@@ -169,7 +178,7 @@ class Trainer:
         last = {}
         for itr in pbar:
             if itr % cfg.eval_interval == 0:
-                tl, vl = self.evaluate(train_s), self.evaluate(val_s)
+                tl, vl = self.evaluate(self.train_eval_sampler), self.evaluate(val_s)
                 postfix.update(train_loss=tl, val_loss=vl)
                 logger.log({"loss/train": tl, "loss/val": vl}, step=itr)
                 last.update(train_loss=tl, val_loss=vl)
@@ -193,7 +202,8 @@ class Trainer:
                             "peak_mem_GB": (torch.cuda.max_memory_allocated() / 2 ** 30) if m.device.type == "cuda" else 0.0},
                            step=itr)
             if mngr is not None:
-                mngr.save(itr, eng, extra={"sampler": train_s.state_dict()})
+                if mngr.save(itr, eng, extra={"sampler": loader.state_dict()}):
+                    logger.log({"ckpt_save_stall_ms": mngr.last_save_stall_ms}, step=itr)
             postfix.update(loss=loss_v, lr=lr, thpt=self.tokens_per_step / self.T / (ms * 1e-3))
             if hasattr(pbar, "set_postfix"):
                 pbar.set_postfix(**postfix)

@@ -98,3 +98,49 @@ def test_sharded_save_then_restore_on_one_process(tmp_path):
     for k, v in outs[0].items():
         assert torch.equal(got[k], torch.as_tensor(v)), k
     assert tr.engine.count == 2
+
+
+def test_orbax_shaped_metadata_schema(tmp_path):
+    """Pins the on-disk schema (layout.py documents where each field comes from)."""
+    import json
+    import msgpack
+    cfg = _tiny_cfg(False)
+    tr = _trainer(cfg)
+    m = CheckpointManager(str(tmp_path), async_save=False)
+    m.save(0, tr.engine, force=True)
+    item = tmp_path / "0" / "default"
+    meta = json.load(open(item / "_METADATA"))
+    assert meta["use_zarr3"] is False and len(meta["tree_metadata"]) == 22 + 18
+    e = meta["tree_metadata"]["('0', '5')"]                          # c_attn
+    assert e["key_metadata"] == [{"key": "0", "key_type": 1}, {"key": "5", "key_type": 1}]
+    assert e["value_metadata"] == {"value_type": "jax.Array", "skip_deserialize": False}
+    assert meta["tree_metadata"]["('1', '0')"]["value_metadata"]["value_type"] == "scalar"     # Adam count
+    agg = msgpack.unpackb(open(item / "checkpoint", "rb").read())
+    assert set(agg) == {"0", "1"} and len(agg["0"]) == 22 and len(agg["1"]) == 18
+    assert agg["0"]["5"] == "PLACEHOLDER://0.5" and agg["0"]["21"] == cfg.model_config.n_layer and agg["1"]["17"] == 0
+    za = json.load(open(item / "0.5" / ".zarray"))
+    L, D = cfg.model_config.n_layer, cfg.model_config.n_embd
+    assert za["shape"] == [L, 3 * D, D] and za["chunks"] == [1, 3 * D, D] and za["compressor"] is None
+
+
+def _save_no_collective(rank, world, d):
+    """Saving must not move tensor data through collectives: every rank writes only the bytes it owns."""
+    import midgpt_b200.parallel.dist as D
+    cfg = _tiny_cfg(True)
+    tr = _trainer(cfg)
+    called = []
+    orig = D.all_gather_flat
+    D.all_gather_flat = lambda *a, **k: (called.append(1), orig(*a, **k))[1]
+    m = CheckpointManager(d, async_save=True)
+    m.save(0, tr.engine, force=True, extra={"sampler": {"rank": rank}})
+    m.wait_until_finished()
+    torch.distributed.barrier()
+    D.all_gather_flat = orig
+    ex = m.restore(0, tr.engine)
+    return len(called), ex
+
+
+def test_save_uses_no_all_gather_and_keeps_per_rank_extra(tmp_path):
+    outs = run_distributed(_save_no_collective, 2, str(tmp_path))
+    assert [o[0] for o in outs] == [0, 0]
+    assert [o[1]["sampler"]["rank"] for o in outs] == [0, 1]

@@ -38,3 +38,12 @@ def test_prepare_launch_resume_sample(tmp_path):
     assert (run / "6" / "default" / "checkpoint").exists() and not (run / "3").exists()   # max_to_keep=1
     out3 = _run(["sample.py", f"--ckpt_dir={run}", "--num_samples=2", "--max_new_tokens=8", "--device=cpu"])
     assert out3.count("---------------") == 2
+
+
+def test_strip_nproc_both_spellings():
+    sys.path.insert(0, ROOT)
+    import launch
+    assert launch.strip_nproc(["--config=a", "--nproc", "8", "--rundir", "r"]) == ["--config=a", "--rundir", "r"]
+    assert launch.strip_nproc(["--nproc=8", "--config=a"]) == ["--config=a"]
+    args = launch.parse_args(launch.strip_nproc(["--config", "shakespeare_char", "--nproc", "2", "--debug"]))
+    assert args.config == "shakespeare_char" and args.debug and args.nproc == 0

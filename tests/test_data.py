@@ -42,3 +42,49 @@ def test_pinned_loader_cpu():
     x, y = ld.next()
     assert x.shape == (4, 32) and x.dtype == torch.int32 and torch.equal(x[:, 1:], y[:, :-1])
     ld.close()
+
+
+def test_loader_state_is_the_consumed_batch_not_the_prefetched_one():
+    """Resume continuity: the background thread runs ahead of the trainer; the checkpointed state must be the
+    one that follows the last batch handed out, so that a restored sampler produces exactly the next batch."""
+    import time
+    data = synthetic_tokens(1 << 16, 1000, seed=2)
+    ld = PinnedBatchLoader(BatchSampler(data, 32, seed=9), 4, torch.device("cpu"), prefetch=2, background=True)
+    for _ in range(3):
+        ld.next()
+    time.sleep(0.2)                       # let the prefetch thread advance the live RNG well past the consumed batch
+    st = ld.state_dict()
+    x4, y4 = ld.next()
+    ld.close()
+    fresh = BatchSampler(data, 32, seed=12345)
+    fresh.load_state_dict(st)
+    fx, fy = fresh.sample(4)
+    assert np.array_equal(fx, x4.numpy()) and np.array_equal(fy, y4.numpy())
+
+
+def test_owt_prepare_streams_in_document_order(tmp_path):
+    """data/openwebtext/prepare.py: bounded-window streaming writes the same bytes as a one-shot concatenation."""
+    import importlib.util, json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "src"; src.mkdir()
+    docs = [f"document {i} " * (1 + i % 7) for i in range(257)]
+    with open(src / "a.jsonl", "w") as f:
+        for d in docs[:200]:
+            f.write(json.dumps({"text": d}) + "\n")
+    for i, d in enumerate(docs[200:]):
+        open(src / f"b{i:03d}.txt", "w").write(d)
+    out = tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(root, "data/openwebtext/prepare.py"), "--source", str(src), "--out", str(out),
+                        "--tokenizer", "bytes", "--workers", "2", "--window", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    train, val = np.fromfile(out / "train.bin", dtype=np.uint16), np.fromfile(out / "val.bin", dtype=np.uint16)
+    spec = importlib.util.spec_from_file_location("owt_prepare", os.path.join(root, "data/openwebtext/prepare.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    order = list(mod.iter_local_docs(str(src)))
+    assert sorted(order) == sorted(docs)
+    n_val = max(1, int(round(len(order) * 0.0005)))
+    val_idx = set(np.random.default_rng(2357).permutation(len(order))[:n_val].tolist())
+    exp_train = np.concatenate([mod._encode(d, "bytes") for i, d in enumerate(order) if i not in val_idx])
+    exp_val = np.concatenate([mod._encode(d, "bytes") for i, d in enumerate(order) if i in val_idx])
+    assert np.array_equal(train, exp_train) and np.array_equal(val, exp_val)
+    assert (train == 50256).sum() + (val == 50256).sum() == len(docs)
