@@ -34,8 +34,36 @@ def timeit(fn, iters=10, warmup=3, flush=None):
     return ts[len(ts) // 2]
 
 
+def gemm_epilogue_bench(be, dev, flush, peak):
+    """Every epilogue variant of the bf16 GEMM on the block shapes of both headline models (M = 32768 tokens)."""
+    r = lambda *s: torch.randn(*s, device=dev, dtype=torch.bfloat16)
+    M = 32768
+    for model, D in (("124M", 768), ("1.5B", 2048)):
+        x, x4 = r(M, D), r(M, 4 * D)
+        w_fc, w_pr = r(4 * D, D) * D ** -0.5, r(D, 4 * D) * (4 * D) ** -0.5
+        w_qkv, w_o = r(3 * D, D) * D ** -0.5, r(D, D) * D ** -0.5
+        acc_fc = torch.zeros(4 * D, D, device=dev)
+        cases = {
+            "store  c_attn   fwd": (lambda: be.linear_fwd(x, w_qkv), 2.0 * M * 3 * D * D),
+            "gelu   c_fc     fwd": (lambda: be.linear_fwd(x, w_fc, act="gelu"), 2.0 * M * 4 * D * D),
+            "resid  mlp_proj fwd": (lambda: be.linear_fwd(x4, w_pr, res=x), 2.0 * M * 4 * D * D),
+            "resid  attn_proj fwd": (lambda: be.linear_fwd(x, w_o, res=x), 2.0 * M * D * D),
+            "store  c_fc     dgrad": (lambda: be.linear_dgrad(x4, w_fc), 2.0 * M * 4 * D * D),
+            "dgelu  mlp_proj dgrad": (lambda: be.linear_dgrad(x, w_pr, gelu_pre=x4), 2.0 * M * 4 * D * D),
+            "f32acc c_fc     wgrad": (lambda: be.linear_wgrad(x4, x, acc_fc), 2.0 * M * 4 * D * D),
+        }
+        for name, (fn, fl) in cases.items():
+            t = timeit(fn, flush=flush)
+            print(json.dumps({"kernel": "gemm_epilogue", "model": model, "case": name, "ms": round(t, 4), "tflops": round(fl / t / 1e9, 1),
+                              "frac_of_cublas_peak": round(fl / (t * 1e-3) / peak, 3)}), flush=True)
+
+
 def main():
     quick = "--quick" in sys.argv
+    if "--gemm-epi" in sys.argv:
+        dev = torch.device("cuda", 0)
+        peak, _ = peak_flops_per_gpu()
+        return gemm_epilogue_bench(B200Backend(dev), dev, torch.empty(256 << 20, dtype=torch.uint8, device=dev), peak)
     dev = torch.device("cuda", 0)
     be = B200Backend(dev)
     peak, how = peak_flops_per_gpu()

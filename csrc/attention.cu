@@ -97,11 +97,13 @@ struct FwdCfg {
   static_assert(BKV == 64, "P is packed over an S row that must already sit in registers (KEEP path)");
 };
 
-template <int C>
+// DROP: attention-probability dropout (reference src/model.py:78) on P in registers, after the row sum l has been taken
+// (dropout acts on the *normalised* probabilities: O = (mask ∘ P / (1-p)) · V, the softmax statistics are untouched).
+template <int C, bool DROP>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
-                int T, int H, float scale) {
+                int T, int H, float scale, uint32_t thr16, float inv_keep, uint2 seed) {
   using Cfg = FwdCfg<C>;
   constexpr int BQ = Cfg::BQ, BKV = Cfg::BKV;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -304,6 +306,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             l += p[e];
           }
         }
+        if (DROP) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const uint32_t keep = dropout_keep8(seed, b * H + h, q_idx, (kv0 + ch * 32) / 8 + g8, thr16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p[8 * g8 + i] = (keep >> i) & 1u ? p[8 * g8 + i] * inv_keep : 0.f;
+          }
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
@@ -419,13 +429,15 @@ struct BwdCfg {
 //   warp 8: TMA producer (K,V once; Q_i/dO_i double buffered)       warp 9: tcgen05.mma issuer
 // Tensor-pipe order per tile:  dV(i) dK(i) dQ(i) | S(i+1) dP(i+1)  — S(i+1) is issued before dQ(i) is drained
 // (dQ aliases dP, not S), so the P phase of the next tile never waits for the tensor core.
-template <int C>
+// DROP: the forward's keep mask is regenerated from the same Philox counters: dV += (mask ∘ P / (1-p))ᵀ · dO and
+// dS = P ∘ (mask / (1-p) ∘ dP − δ) / √C, with δ = Σ dO ∘ O unchanged (O already contains the dropped probabilities).
+template <int C, bool DROP>
 __global__ void __launch_bounds__(BwdCfg<C>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const __grid_constant__ CUtensorMap tmdQ, const float* __restrict__ lse, const float* __restrict__ delta,
                 __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long dkv_row_stride, int T, int H,
-                float scale, int dbg) {
+                float scale, int dbg, uint32_t thr16, float inv_keep, uint2 seed) {
   // dbg (MIDGPT_ATTN_DEBUG, profiling experiments only; results are wrong when set): 1 = skip the dQ reduce-add,
   // 2 = skip the exponentials, 4 = skip the dQ staging stores as well
   using Cfg = BwdCfg<C>;
@@ -622,6 +634,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
+      uint32_t keep[DROP ? 8 : 1];                  // keep[g] bit i: key kv0 + cbase + 8 g + i of this query row survives
+      if (DROP) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) keep[DROP ? g : 0] = dropout_keep8(seed, b * H + h, q_idx, (kv0 + cbase) / 8 + g, thr16);
+      }
       if (it > 0) {
         // the previous tile's dQ reduce-add may still be reading its staging areas (the P/dS buffer and that tile's Q stage):
         // wait for it only now, after this tile's exponentials have been computed, then release the Q/dO stage for refill
@@ -633,8 +650,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        uint4 v4 = make_uint4(pack_bf16(p[8 * g], p[8 * g + 1]), pack_bf16(p[8 * g + 2], p[8 * g + 3]),
-                              pack_bf16(p[8 * g + 4], p[8 * g + 5]), pack_bf16(p[8 * g + 6], p[8 * g + 7]));
+        float pd[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pd[i] = DROP ? ((keep[DROP ? g : 0] >> i) & 1u ? p[8 * g + i] * inv_keep : 0.f) : p[8 * g + i];
+        uint4 v4 = make_uint4(pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]), pack_bf16(pd[6], pd[7]));
         st_swizzled_chunk(sPS, 128, row, half * 8 + g, v4);
       }
       tc_fence_before();
@@ -650,8 +669,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          p[e] *= fmaf(__uint_as_float(d0[e]), scale, -dsc);
-          p[32 + e] *= fmaf(__uint_as_float(d1[e]), scale, -dsc);
+          float s0 = scale, s1 = scale;
+          if (DROP) {
+            s0 = (keep[DROP ? e / 8 : 0] >> (e & 7)) & 1u ? scale * inv_keep : 0.f;
+            s1 = (keep[DROP ? 4 + e / 8 : 0] >> (e & 7)) & 1u ? scale * inv_keep : 0.f;
+          }
+          p[e] *= fmaf(__uint_as_float(d0[e]), s0, -dsc);
+          p[32 + e] *= fmaf(__uint_as_float(d1[e]), s1, -dsc);
         }
       }
       mbar_wait(dv_done, ph);
@@ -755,8 +779,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   likewise) | dQᵀ 192..255 | dV 256..383 | dK 384..511
 //   warps 0-7 softmax (thread = key row × 32-query half), 8-11 output (dQ drain, dV/dK), 12 TMA producer, 13 MMA issuer.
 // ================================================================================================
+template <int C_>
 struct Bwd3Cfg {
-  static constexpr int C = 128, BQ = 64;
+  static constexpr int C = C_, BQ = 64;
   static constexpr int KV_TILE = 128 * C * 2;          // K or V   [128 x C] bf16
   static constexpr int Q_TILE = BQ * C * 2;            // Q or dO  [64 x C] bf16
   static constexpr int NQ = 3, NDO = 2;                // pipeline depth of the Q and dO stages
@@ -764,20 +789,21 @@ struct Bwd3Cfg {
   static constexpr int STG = BQ * C * 4;               // dQ staging [64 queries x C] fp32, 2 buffers; they double as the dV / dK output tiles
   static constexpr int STAT = 2 * BQ * 4;              // lse·log2e | delta·scale of one query tile
   static constexpr int SMEM = 2 * KV_TILE + (NQ + NDO) * Q_TILE + DS + 2 * STG + NQ * STAT + 512;   // + barriers, item ring
-  static constexpr int ST_COL = 0, DPT_COL = 64, DQT_COL = 192, DV_COL = 256, DK_COL = 384;   // dPᵀ: 2 buffers of 64 columns
+  static constexpr int ST_COL = 0, DPT_COL = 64, DQT_COL = 192, DV_COL = 256, DK_COL = 256 + C;   // dPᵀ: 2 buffers of 64 columns
   static constexpr int NSW = 8, NDW = 4;               // softmax warps (P, dS), output warps (dQ drain, dV/dK epilogue)
   static constexpr int NST = 32 * NSW, NDT = 32 * NDW;
   static constexpr int THREADS = NST + NDT + 64;       // + TMA warp + MMA warp
   static constexpr int CPT = 64 * 4 / NSW;             // query columns per softmax thread: 4 lane quarters x 2 column groups
 };
 
-__global__ void __launch_bounds__(Bwd3Cfg::THREADS, 1)
+template <int C_>
+__global__ void __launch_bounds__(Bwd3Cfg<C_>::THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                  const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
                  const __grid_constant__ CUtensorMap tmdV, const float* __restrict__ lse2, const float* __restrict__ dsc,
                  int T, int H, int n_items, int* __restrict__ sched, float scale, int dbg) {
-  using Cfg = Bwd3Cfg;
+  using Cfg = Bwd3Cfg<C_>;
   constexpr int C = Cfg::C, CPT = Cfg::CPT;
   constexpr int W_OUT = Cfg::NSW, W_TMA = Cfg::NSW + Cfg::NDW, W_MMA = W_TMA + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -896,7 +922,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     {
       constexpr uint32_t idesc_st = make_idesc_bf16(128, 64, 0, 0);    // Sᵀ, dPᵀ: A = K / V (K-major), B = Q / dO (K-major), N = 64
       constexpr uint32_t idesc_ts = make_idesc_bf16(128, C, 0, 1);     // dV, dK : A in TMEM, B = dO / Q MN-major, N = C
-      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);    // dQᵀ    : A = Kᵀ (MN-major), B = dSᵀ tile (MN-major), N = 64
+      constexpr uint32_t idesc_dq = make_idesc_bf16(C, 64, 1, 1);      // dQᵀ    : A = Kᵀ (MN-major, M = head_dim), B = dSᵀ tile (MN-major), N = 64
       // descriptors are built once; per MMA only a 64-bit add of a compile-time offset (see desc_shift)
       const uint64_t k_k = make_smem_desc(smem_u32(sK), 16, 1024), v_k = make_smem_desc(smem_u32(sV), 16, 1024);       // K-major views
       const uint64_t q_k0 = make_smem_desc(smem_u32(sQ), 16, 1024), do_k0 = make_smem_desc(smem_u32(sdO), 16, 1024);
@@ -1000,7 +1026,6 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const bool issuer = (warp == W_OUT && lane == 0);
-    const int l4 = lane >> 2;
     int g = 0;
     for (int ic = 0;; ++ic) {
       const int w = next_item(ic);
@@ -1022,18 +1047,25 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           else tma_wait_group_read<1>();
         }
         named_bar_sync(1, Cfg::NDT);
-        uint8_t* stg = sStg + (g & 1) * Cfg::STG + quarter * (64 * 128) + (lane & 3) * 4;
+        // head-dim index of this lane's accumulator row.  M = 128: lane i of the CTA holds row i.  M = 64 (head_dim 64): the
+        // accumulator occupies the first 16 lanes of every 32-lane quarter, row = 16 * quarter + lane (cute tmem_frg_1sm, M_MMA = 64).
+        const int d = (C == 128) ? row : quarter * 16 + (lane & 15);
+        const bool d_valid = (C == 128) || lane < 16;
+        const int d4 = (d & 31) >> 2;              // 16-byte chunk of the 32-column box
+        uint8_t* stg = sStg + (g & 1) * Cfg::STG + (d >> 5) * (64 * 128) + (d & 3) * 4;
+        if (d_valid) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          *reinterpret_cast<uint32_t*>(stg + e * 128 + ((l4 ^ (e & 7)) << 4)) = dq0[e];
-          *reinterpret_cast<uint32_t*>(stg + (32 + e) * 128 + ((l4 ^ (e & 7)) << 4)) = dq1[e];
+          for (int e = 0; e < 32; ++e) {
+            *reinterpret_cast<uint32_t*>(stg + e * 128 + ((d4 ^ (e & 7)) << 4)) = dq0[e];
+            *reinterpret_cast<uint32_t*>(stg + (32 + e) * 128 + ((d4 ^ (e & 7)) << 4)) = dq1[e];
+          }
         }
         fence_proxy_async_smem();
         named_bar_sync(1, Cfg::NDT);
         if (issuer) {
           if (!(dbg & 1))                          // MIDGPT_ATTN_DEBUG=1: what-if without the reduce-add (wrong dQ)
 #pragma unroll
-          for (int bx = 0; bx < 4; ++bx) tma_reduce_add_3d(&tmdQ, sStg + (g & 1) * Cfg::STG + bx * (64 * 128), h * C + bx * 32, kv0 + j * 64, b);
+          for (int bx = 0; bx < C / 32; ++bx) tma_reduce_add_3d(&tmdQ, sStg + (g & 1) * Cfg::STG + bx * (64 * 128), h * C + bx * 32, kv0 + j * 64, b);
           tma_commit_group();
         }
       }
@@ -1045,7 +1077,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (issuer) tma_wait_group_read<1>();
       named_bar_sync(1, Cfg::NDT);
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < C / 32; ++ch) {
         uint32_t r[32];
         tmem_ld_x32(t_lane + Cfg::DV_COL + ch * 32, r);
         tmem_ld_wait();
@@ -1057,9 +1089,9 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                        pack_bf16(__uint_as_float(r[8 * q4 + 4]), __uint_as_float(r[8 * q4 + 5])),
                                        pack_bf16(__uint_as_float(r[8 * q4 + 6]), __uint_as_float(r[8 * q4 + 7]))));
       }
-      uint32_t kk[64];
+      uint32_t kk[C / 2];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < C / 32; ++ch) {
         uint32_t r[32];
         tmem_ld_x32(t_lane + Cfg::DK_COL + ch * 32, r);
         tmem_ld_wait();
@@ -1072,19 +1104,19 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       named_bar_sync(1, Cfg::NDT);
       if (issuer) {
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) tma_store_4d(&tmdV, tile_v + cb * (128 * 128), cb * 64, h, kv0, b);
+        for (int cb = 0; cb < C / 64; ++cb) tma_store_4d(&tmdV, tile_v + cb * (128 * 128), cb * 64, h, kv0, b);
         tma_commit_group();
         tma_wait_group_read<1>();                  // everything but the dV store: the last reduce-add has left tile_k
       }
       named_bar_sync(1, Cfg::NDT);
 #pragma unroll
-      for (int cc = 0; cc < 16; ++cc)
+      for (int cc = 0; cc < C / 8; ++cc)
         st_swizzled_chunk(tile_k, 128, row, cc, make_uint4(kk[4 * cc], kk[4 * cc + 1], kk[4 * cc + 2], kk[4 * cc + 3]));
       fence_proxy_async_smem();
       named_bar_sync(1, Cfg::NDT);
       if (issuer) {
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) tma_store_4d(&tmdK, tile_k + cb * (128 * 128), cb * 64, h, kv0, b);
+        for (int cb = 0; cb < C / 64; ++cb) tma_store_4d(&tmdK, tile_k + cb * (128 * 128), cb * 64, h, kv0, b);
         tma_commit_group();
       }
     }
@@ -1194,26 +1226,43 @@ static void check(const char* what) {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, int C, long long q_row_stride,
-              long long k_row_stride, long long v_row_stride, int num_sms, cudaStream_t s) {
+struct DropArgs {
+  uint32_t thr16;      // round(p * 65536); 0 = no dropout
+  float inv_keep;
+  uint2 seed;
+};
+static DropArgs drop_args(float p_drop, unsigned long long seed) {
+  if (p_drop < 0.f || p_drop >= 1.f) throw std::runtime_error("attention: dropout probability must be in [0, 1)");
+  DropArgs d;
+  d.thr16 = static_cast<uint32_t>(lrintf(p_drop * 65536.f));
+  d.inv_keep = 1.f / (1.f - static_cast<float>(d.thr16) / 65536.f);
+  d.seed = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  return d;
+}
+
+template <int C, bool DROP>
+static void launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, long long q_row_stride,
+                       long long k_row_stride, long long v_row_stride, const DropArgs& d, cudaStream_t s) {
+  using Cfg = FwdCfg<C>;
   const float scale = 1.f / sqrtf(static_cast<float>(C));
   dim3 grid((T + 127) / 128, H, B);
+  CUtensorMap tq = make_tmap_bthc(q, B, T, H, C, q_row_stride, Cfg::BQ), tk = make_tmap_bthc(k, B, T, H, C, k_row_stride, Cfg::BKV),
+              tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, Cfg::BKV);
+  static bool once = (set_smem(attn_fwd_kernel<C, DROP>, Cfg::SMEM), true);
+  (void)once;
+  attn_fwd_kernel<C, DROP><<<grid, 192, Cfg::SMEM, s>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, T, H, scale, d.thr16, d.inv_keep, d.seed);
+}
+
+void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, int C, long long q_row_stride,
+              long long k_row_stride, long long v_row_stride, float p_drop, unsigned long long seed, int num_sms, cudaStream_t s) {
+  const DropArgs d = drop_args(p_drop, seed);
+  if (C != 64 && C != 128) throw std::runtime_error("attention: head_dim must be 64 or 128");
   if (C == 64) {
-    using Cfg = FwdCfg<64>;
-    CUtensorMap tq = make_tmap_bthc(q, B, T, H, C, q_row_stride, Cfg::BQ), tk = make_tmap_bthc(k, B, T, H, C, k_row_stride, Cfg::BKV),
-                tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, Cfg::BKV);
-    static bool once = (set_smem(attn_fwd_kernel<64>, Cfg::SMEM), true);
-    (void)once;
-    attn_fwd_kernel<64><<<grid, 192, Cfg::SMEM, s>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, T, H, scale);
-  } else if (C == 128) {
-    using Cfg = FwdCfg<128>;
-    CUtensorMap tq = make_tmap_bthc(q, B, T, H, C, q_row_stride, Cfg::BQ), tk = make_tmap_bthc(k, B, T, H, C, k_row_stride, Cfg::BKV),
-                tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, Cfg::BKV);
-    static bool once = (set_smem(attn_fwd_kernel<128>, Cfg::SMEM), true);
-    (void)once;
-    attn_fwd_kernel<128><<<grid, 192, Cfg::SMEM, s>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, T, H, scale);
+    if (d.thr16) launch_fwd<64, true>(q, k, v, o, lse, B, T, H, q_row_stride, k_row_stride, v_row_stride, d, s);
+    else launch_fwd<64, false>(q, k, v, o, lse, B, T, H, q_row_stride, k_row_stride, v_row_stride, d, s);
   } else {
-    throw std::runtime_error("attention: head_dim must be 64 or 128");
+    if (d.thr16) launch_fwd<128, true>(q, k, v, o, lse, B, T, H, q_row_stride, k_row_stride, v_row_stride, d, s);
+    else launch_fwd<128, false>(q, k, v, o, lse, B, T, H, q_row_stride, k_row_stride, v_row_stride, d, s);
   }
   check("attn_fwd");
 }
@@ -1231,8 +1280,9 @@ static int* sched_counter(cudaStream_t s) {
 
 void attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* delta, void* dq,
               void* dk, void* dv, float* dq_accum, int B, int T, int H, int C, long long q_row_stride, long long k_row_stride,
-              long long v_row_stride, long long dqkv_row_stride, int num_sms, cudaStream_t s) {
+              long long v_row_stride, long long dqkv_row_stride, float p_drop, unsigned long long seed, int num_sms, cudaStream_t s) {
   const float scale = 1.f / sqrtf(static_cast<float>(C));
+  const DropArgs d = drop_args(p_drop, seed);
   const long long nvec = static_cast<long long>(B) * T * H;
   if (nvec >= (1ll << 31)) throw std::runtime_error("attention: too many (token, head) vectors for 32-bit indexing");
   if (C == 64)
@@ -1248,28 +1298,38 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
   CUtensorMap tdq = make_tmap_dq(dq_accum, B, T, H * C);
   static const int dbg = [] { const char* e = getenv("MIDGPT_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
   static const bool use_v2 = [] { const char* e = getenv("MIDGPT_ATTN_BWD"); return e && std::string(e) == "v2"; }();
-  if (C == 128 && T % 64 == 0 && !use_v2) {
+  // dropout: the transposed (v3) kernel's threads own one key and 32 queries, i.e. one Philox call per element instead of
+  // one per eight; the row-major v2 kernel regenerates the forward's mask at the forward's cost, so it serves p > 0.
+  if (T % 64 == 0 && !use_v2 && d.thr16 == 0) {
     CUtensorMap tq64 = make_tmap_bthc(q, B, T, H, C, q_row_stride, 64), tdo64 = make_tmap_bthc(dout, B, T, H, C, static_cast<long long>(H) * C, 64);
     CUtensorMap tdq64 = make_tmap_dq(dq_accum, B, T, H * C, 64);
     const size_t plane = static_cast<size_t>(B) * H * T;          // delta planes: raw | delta*scale | lse*log2e (attn_bwd_prep_kernel)
     CUtensorMap tdk = make_tmap_bthc(dk, B, T, H, C, dqkv_row_stride, 128), tdv = make_tmap_bthc(dv, B, T, H, C, dqkv_row_stride, 128);
-    static bool once = (set_smem(attn_bwd3_kernel, Bwd3Cfg::SMEM), true);
-    (void)once;
     const int n_items = static_cast<int>(grid.x) * H * B;         // persistent: one CTA per SM pulls items off a global counter
-    attn_bwd3_kernel<<<std::min(num_sms, n_items), Bwd3Cfg::THREADS, Bwd3Cfg::SMEM, s>>>(tq64, tk, tv, tdo64, tdq64, tdk, tdv, delta + 2 * plane, delta + plane,
-                                                                                      T, H, n_items, sched_counter(s), scale, dbg);
-  } else if (C == 64) {
-    static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
-    (void)once;
-    attn_bwd_kernel<64><<<grid, BwdCfg<64>::THREADS, BwdCfg<64>::SMEM, s>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk),
-                                                                             static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale, dbg);
-  } else if (C == 128) {
-    static bool once = (set_smem(attn_bwd_kernel<128>, BwdCfg<128>::SMEM), true);
-    (void)once;
-    attn_bwd_kernel<128><<<grid, BwdCfg<128>::THREADS, BwdCfg<128>::SMEM, s>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk),
-                                                                               static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale, dbg);
+    if (C == 128) {
+      static bool once = (set_smem(attn_bwd3_kernel<128>, Bwd3Cfg<128>::SMEM), true);
+      (void)once;
+      attn_bwd3_kernel<128><<<std::min(num_sms, n_items), Bwd3Cfg<128>::THREADS, Bwd3Cfg<128>::SMEM, s>>>(
+          tq64, tk, tv, tdo64, tdq64, tdk, tdv, delta + 2 * plane, delta + plane, T, H, n_items, sched_counter(s), scale, dbg);
+    } else {
+      static bool once = (set_smem(attn_bwd3_kernel<64>, Bwd3Cfg<64>::SMEM), true);
+      (void)once;
+      attn_bwd3_kernel<64><<<std::min(num_sms, n_items), Bwd3Cfg<64>::THREADS, Bwd3Cfg<64>::SMEM, s>>>(
+          tq64, tk, tv, tdo64, tdq64, tdk, tdv, delta + 2 * plane, delta + plane, T, H, n_items, sched_counter(s), scale, dbg);
+    }
   } else {
-    throw std::runtime_error("attention: head_dim must be 64 or 128");
+#define MG_BWD2(CC, DR)                                                                                                              \
+    {                                                                                                                                \
+      static bool once = (set_smem(attn_bwd_kernel<CC, DR>, BwdCfg<CC>::SMEM), true);                                                \
+      (void)once;                                                                                                                    \
+      attn_bwd_kernel<CC, DR><<<grid, BwdCfg<CC>::THREADS, BwdCfg<CC>::SMEM, s>>>(tq, tk, tv, tdo, tdq, lse, delta,                  \
+          static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), dqkv_row_stride, T, H, scale, dbg, d.thr16, d.inv_keep, d.seed); \
+    }
+    if (C == 64 && d.thr16) MG_BWD2(64, true)
+    else if (C == 64) MG_BWD2(64, false)
+    else if (d.thr16) MG_BWD2(128, true)
+    else MG_BWD2(128, false)
+#undef MG_BWD2
   }
   check("attn_bwd");
   dq_convert_kernel<<<num_sms * 8, 256, 0, s>>>(dq_accum, static_cast<__nv_bfloat16*>(dq), static_cast<long long>(B) * T, H * C, dqkv_row_stride);

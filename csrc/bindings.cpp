@@ -35,10 +35,11 @@ void sumsq_accumulate(const float* g, long long n, float* out, int num_sms, cuda
 void adamw_step(float* p, float* m, float* v, float* g, void* p_lp, long long n, const float* clip_ptr, float lr, float b1,
                 float b2, float eps, float wd_over_lr_peak, float bc1, float bc2, int zero_grad, int num_sms, cudaStream_t s);
 void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, int C, long long q_row_stride,
-              long long kv_row_stride_k, long long kv_row_stride_v, int num_sms, cudaStream_t s);
+              long long kv_row_stride_k, long long kv_row_stride_v, float p_drop, unsigned long long seed, int num_sms, cudaStream_t s);
 void attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, float* delta,
               void* dq, void* dk, void* dv, float* dq_accum, int B, int T, int H, int C, long long q_row_stride,
-              long long k_row_stride, long long v_row_stride, long long dqkv_row_stride, int num_sms, cudaStream_t s);
+              long long k_row_stride, long long v_row_stride, long long dqkv_row_stride, float p_drop, unsigned long long seed,
+              int num_sms, cudaStream_t s);
 void xrank_barrier(const long long* pad_ptrs, int rank, int world, int slot, unsigned epoch, cudaStream_t s);
 void rs_sumsq(const long long* grad_ptrs, long long mc_ptr, float* out_shard, float* sumsq, long long shard_off, long long n, int rank,
               int world, int num_sms, cudaStream_t s);
@@ -266,7 +267,8 @@ void adamw_step(at::Tensor& p, at::Tensor& m, at::Tensor& v, at::Tensor& g, cons
 }
 
 // q,k: [B,T,H,C] views with arbitrary row (token) stride; v likewise; returns (o [B*T, H*C], lse [B,H,T]).
-std::vector<at::Tensor> attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v) {
+// dropout_p > 0: attention-probability dropout inside the kernel (Philox keyed by seed; the backward regenerates the mask).
+std::vector<at::Tensor> attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, double dropout_p, int64_t seed) {
   c10::cuda::CUDAGuard guard(q.device());
   CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v);
   TORCH_CHECK(q.dim() == 4 && q.stride(3) == 1 && q.stride(2) == q.size(3), "q must be [B,T,H,C] with packed heads");
@@ -276,13 +278,13 @@ std::vector<at::Tensor> attn_fwd(const at::Tensor& q, const at::Tensor& k, const
   auto o = at::empty({B * T, H * C}, q.options());
   auto lse = at::empty({B, H, T}, q.options().dtype(at::kFloat));
   mg::attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), B, T, H, C, q.stride(1), k.stride(1),
-               v.stride(1), num_sms_of(q), stream());
+               v.stride(1), static_cast<float>(dropout_p), static_cast<unsigned long long>(seed), num_sms_of(q), stream());
   return {o, lse};
 }
 
 // dqkv: [B*T, 3*H*C] bf16 output (dq | dk | dv thirds).
 at::Tensor attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& o, const at::Tensor& dout,
-                    const at::Tensor& lse) {
+                    const at::Tensor& lse, double dropout_p, int64_t seed) {
   c10::cuda::CUDAGuard guard(q.device());
   CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(o); CHECK_BF16(dout); CHECK_F32(lse);
   const int64_t B = q.size(0), T = q.size(1), H = q.size(2), C = q.size(3);
@@ -293,7 +295,7 @@ at::Tensor attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& 
   char* base = static_cast<char*>(dqkv.data_ptr());
   mg::attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(),
                base, base + H * C * 2, base + 2 * H * C * 2, dq_accum.data_ptr<float>(), B, T, H, C, q.stride(1), k.stride(1), v.stride(1),
-               3 * H * C, num_sms_of(q), stream());
+               3 * H * C, static_cast<float>(dropout_p), static_cast<unsigned long long>(seed), num_sms_of(q), stream());
   return dqkv;
 }
 

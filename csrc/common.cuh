@@ -70,6 +70,36 @@ MG_DEVICE float gelu_tanh_grad(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) and the attention-dropout keep mask derived from it.
+// One call yields 128 random bits = eight 16-bit lanes: element (bh, q, k) of the attention-probability matrix uses lane
+// k & 7 of the call with counter (k >> 3, q, bh, tag), so any kernel whose threads own >= 8 consecutive keys of one query
+// row (forward: a row; backward v2: half a row) regenerates exactly the same mask with one call per 8 elements.
+// ------------------------------------------------------------------------------------------------
+MG_DEVICE uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// bit i set <=> element k = 8 * k8 + i of row q is KEPT; thr16 = round(p_drop * 65536): P(drop) = thr16 / 65536
+MG_DEVICE uint32_t dropout_keep8(uint2 key, uint32_t bh, uint32_t q, uint32_t k8, uint32_t thr16) {
+  const uint4 r = philox4x32_10(make_uint4(k8, q, bh, 0x0a77d209u), key);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m |= ((w[i] & 0xFFFFu) >= thr16 ? 1u : 0u) << (2 * i);
+    m |= ((w[i] >> 16) >= thr16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 MG_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {

@@ -12,8 +12,8 @@
 //   warp 0   TMA producer   (one elected lane)
 //   warp 1   TMEM allocator + tcgen05.mma issuer (one elected lane)
 //   warp 2-9 epilogue: TMEM -> registers -> epilogue math -> smem staging -> TMA store / reduce-add.
-//            Two warps share each TMEM lane quarter and split every column chunk in half, so each SM
-//            sub-partition has two epilogue warps to hide tcgen05.ld / MUFU latency behind each other.
+//            Two warps share each TMEM lane quarter and take alternate column chunks; every warp owns a
+//            32-row staging box and issues its own TMA stores -- no barrier couples the epilogue warps.
 // Pipelines: smem ring (full/empty mbarriers, 4 stages of 128x64 A + 256x64 B), TMEM ring (2 x 256 columns).
 #include "common.cuh"
 
@@ -117,22 +117,30 @@ struct WorkIter {
   }
 };
 
-template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false, bool CG2 = false>
+template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false, bool CG2 = false, bool AUXB = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                   const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int NST = CG2 ? 6 : STAGES;                          // pipeline depth
+  // Pair kernels whose epilogue reads a second [M, N] operand (residual / pre-activation) or writes a second output (gelu)
+  // move that tile by TMA through a second 4 KB box per epilogue warp (AUXBUF) and give up one of the six operand stages for it:
+  // 16-byte-per-lane global accesses with one row per lane cost 32 L1 wavefronts per instruction, and those wavefronts compete
+  // with the tensor core's operand reads for the same shared-memory / L1 bandwidth.
+  constexpr bool HAS_AUX = (EPI == EPI_RESIDUAL || EPI == EPI_DGELU);
+  constexpr bool AUXBUF = CG2 && AUXB && (HAS_AUX || EPI == EPI_GELU);
+  constexpr int NST = CG2 ? (AUXBUF ? 5 : 6) : STAGES;           // pipeline depth
   constexpr int STG = CG2 ? 2 * A_STAGE_BYTES : STAGE_BYTES;     // bytes per stage in this CTA (A 16 KB + B 16 KB (half) | 32 KB)
-  static_assert(NST * STG == STAGES * STAGE_BYTES, "operand ring must end where the epilogue staging begins");
-  uint8_t* sC = smem + NST * STG;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + 2 * CSTAGE_BYTES);
+  static_assert(NST * STG + (AUXBUF ? 8 * 4096 : 0) == STAGES * STAGE_BYTES, "operand ring (+ aux boxes) must end where the barriers begin");
+  uint8_t* sC = smem + NST * STG;                                // 8 x 4 KB staging boxes
+  uint8_t* sAux = sC + 8 * 4096;                                 // 8 x 4 KB aux boxes (AUXBUF only)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES);
   uint64_t* empty_bar = full_bar + NST;
   uint64_t* tfull_bar = empty_bar + NST;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = full_bar + 24;                             // [8] one per epilogue warp (AUXBUF only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,11 +155,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
-    if (EPI == EPI_GELU) tma_prefetch_desc(&tmD2);
+    if (AUXBUF) tma_prefetch_desc(&tmD2);
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    if (AUXBUF)
+      for (int w = 0; w < 8; ++w) mbar_init(&aux_bar[w], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], CG2 ? 2 * EPI_THREADS : EPI_THREADS);     // CG2: the leader waits for both CTAs' epilogues
@@ -383,11 +393,32 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue warps =====================
+    // Every warp is its own pipeline: it owns a 32-row x 128-byte (4 KB) staging box and issues its own TMA stores, so no
+    // barrier ever couples the eight warps (round 1 synchronised all 256 threads twice per 64-column chunk and a single thread
+    // issued every store: with K = 768 -- 12 k-blocks per tile -- the GELU / DGELU tiles were epilogue-bound at 0.7 PFLOP/s).
+    // Warp (q, half) drains the 64-column (fp32: 32-column) chunks of its TMEM lane quarter whose index has parity `half`;
+    // the operand of the fused element-wise op (residual / pre-activation) is fetched into registers BEFORE the accumulator
+    // wait, and the TMEM buffer is handed back right after this thread's last tcgen05.ld of the tile.
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;             // which half of every column chunk this warp handles
+    const int half = (warp - 2) >> 2;             // chunk parity this warp handles
     const int row = q * 32 + lane;                // row inside the 128-row tile
-    const bool issuer = (threadIdx.x == 64);      // first epilogue thread issues the TMA stores
-    const uint32_t sw = (row & 7);
+    uint8_t* sbuf = sC + (warp - 2) * 4096;       // this warp's staging box (1024-byte aligned: swizzle-128B atom)
+    uint8_t* rowp = sbuf + lane * 128;
+    const uint32_t sw = lane & 7;
+    uint8_t* abuf = sAux + (warp - 2) * 4096;     // AUXBUF: this warp's aux box (TMA-loaded operand, or the gelu output tile)
+    uint64_t* abar = &aux_bar[warp - 2];
+    uint32_t aphase = 0;
+    auto request_aux = [&](int col0, int row0) {  // warp-uniform; boxes entirely outside the matrix are neither requested nor awaited
+      if (lane == 0 && col0 < p.N && row0 < p.M) {
+        mbar_expect_tx(abar, 4096);
+        tma_load_2d(abuf, &tmD2, abar, col0, row0);
+      }
+    };
+    auto load_aux = [&](uint4 (&a)[8], long long grow, int col0) {
+      const uint4* ap = reinterpret_cast<const uint4*>(p.aux + grow * p.ld_aux + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = (grow < p.M && col0 + 8 * j < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
+    };
     int it = 0;
     WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, p.split_k);
     for (int tile, kb0_, kb1_; work.next(tile, kb0_, kb1_); ++it) {
@@ -395,118 +426,150 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tile_coords(tile, m_blk, n_blk);
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
+      const long long grow = static_cast<long long>(m_blk) * BM + row;
+      const int row0 = m_blk * BM + q * 32;       // first row of this warp's box
+      uint4 aux_next[8];
+      if (HAS_AUX && !AUXBUF) load_aux(aux_next, grow, n_blk * BN + half * 64);
+      if (HAS_AUX && AUXBUF) request_aux(n_blk * BN + half * 64, row0);
       mbar_wait(&tfull_bar[buf], tphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
-      const long long grow = static_cast<long long>(m_blk) * BM + row;
 
       if (EPI == EPI_F32) {
-        // 8 chunks of 32 fp32 columns (128 B per row); each warp of a pair moves 16 of them
+        // 8 chunks of 32 fp32 columns (128 B per row); this warp moves the 4 of its parity
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint8_t* sbuf = sC + (c & 1) * CSTAGE_BYTES;
-          if (issuer) tma_wait_group_read<1>();
-          named_bar_sync(1, EPI_THREADS);
-          uint32_t r[16];
-          tmem_ld_x16(t_row + c * 32 + half * 16, r);
+        for (int c = half; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c * 32, r);
           tmem_ld_wait();
-          uint8_t* rowp = sbuf + row * 128;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = v;
+          if (c + 2 >= BN / 32) {               // last TMEM read of this tile by this thread
+            tc_fence_before();
+            if (CG2) mbar_arrive_cluster(mapa_rank0(smem_u32(&tempty_bar[buf])));
+            else mbar_arrive(&tempty_bar[buf]);
           }
+          if (lane == 0) tma_wait_group_read<0>();      // the previous store has finished reading the staging box
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           fence_proxy_async_smem();
-          named_bar_sync(2, EPI_THREADS);
-          if (issuer) {
+          __syncwarp();
+          if (lane == 0) {
             const int c0 = n_blk * BN + c * 32;
-            if (c0 < p.N) {
-              if (p.accumulate) tma_reduce_add_2d(&tmD, sbuf, c0, m_blk * BM);
-              else tma_store_2d(&tmD, sbuf, c0, m_blk * BM);
+            if (c0 < p.N && row0 < p.M) {
+              if (p.accumulate) tma_reduce_add_2d(&tmD, sbuf, c0, row0);
+              else tma_store_2d(&tmD, sbuf, c0, row0);
             }
             tma_commit_group();
           }
         }
       } else {
-        // 4 chunks of 64 bf16 columns (128 B per row); each warp of a pair converts 32 of them
+        // 4 chunks of 64 bf16 columns (128 B per row); this warp converts the 2 of its parity
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          uint8_t* sbuf = sC + (c & 1) * CSTAGE_BYTES;
-          if (issuer) tma_wait_group_read<1>();
-          named_bar_sync(1, EPI_THREADS);
-          uint32_t r[32];
-          tmem_ld_x32(t_row + c * 64 + half * 32, r);
-          tmem_ld_wait();
+        for (int c = half; c < BN / 64; c += 2) {
           const int col0 = n_blk * BN + c * 64;
-          const bool valid = (grow < p.M) && (col0 < p.N);
+          uint4 aux[8];
+          if (HAS_AUX && !AUXBUF) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) aux[j] = aux_next[j];
+          }
+          uint32_t r[64];
+          {
+            uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+            uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
+            tmem_ld_x32(t_row + c * 64, r0);
+            tmem_ld_x32(t_row + c * 64 + 32, r1);
+          }
+          if (HAS_AUX && !AUXBUF && c + 2 < BN / 64) load_aux(aux_next, grow, col0 + 128);     // next chunk's operand while TMEM answers
+          const bool have_box = col0 < p.N && row0 < p.M;       // warp-uniform
+          if (HAS_AUX && AUXBUF && have_box) {
+            mbar_wait(abar, aphase);
+            aphase ^= 1;
+          }
+          tmem_ld_wait();
+          if (c + 2 >= BN / 64) {               // last TMEM read of this tile by this thread
+            tc_fence_before();
+            if (CG2) mbar_arrive_cluster(mapa_rank0(smem_u32(&tempty_bar[buf])));
+            else mbar_arrive(&tempty_bar[buf]);
+          }
           if (FP8) {
             const float sa = grow < p.M ? __ldg(p.row_scale_a + grow) : 0.f;
-            const float4* sb4 = reinterpret_cast<const float4*>(p.row_scale_b + col0 + half * 32);
+            const float4* sb4 = reinterpret_cast<const float4*>(p.row_scale_b + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 sb = (col0 + half * 32 + 4 * j < p.N) ? __ldg(sb4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 16; ++j) {
+              const float4 sb = (col0 + 4 * j < p.N) ? __ldg(sb4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
               r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * sa * sb.x);
               r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * sa * sb.y);
               r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * sa * sb.z);
               r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * sa * sb.w);
             }
           }
-          uint8_t* rowp = sbuf + row * 128;
-          if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + grow * p.ld_aux + col0) + half * 4;
+          if (lane == 0) tma_wait_group_read<0>();      // the previous store(s) have finished reading the staging box(es)
+          __syncwarp();
+          // two halves of 32 columns: operand -> math -> staging, so that only the accumulator chunk stays live in registers
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 a = valid ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
-              uint32_t au[4] = {a.x, a.y, a.z, a.w};
-              uint32_t o[4];
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[16];
+            if (HAS_AUX) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 av = unpack_bf16(au[e]);
-                float x0 = __uint_as_float(r[8 * j + 2 * e]), x1 = __uint_as_float(r[8 * j + 2 * e + 1]);
-                if (EPI == EPI_RESIDUAL) { x0 += av.x; x1 += av.y; }
-                else { x0 *= gelu_tanh_grad(av.x); x1 *= gelu_tanh_grad(av.y); }
-                o[e] = pack_bf16(x0, x1);
-              }
-              *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-          } else {
-            // GELU: the pre-activation goes through the staged TMA store, gelu(pre) straight from registers to global memory
-            // (64 contiguous bytes per thread) so the two staging buffers keep double-buffering the chunks
-            __nv_bfloat16* d2row = (EPI == EPI_GELU) ? p.d2 + grow * p.ldd2 + col0 + half * 32 : nullptr;
+              for (int j = 0; j < 4; ++j) {
+                uint4 a4;
+                if (AUXBUF) a4 = have_box ? *reinterpret_cast<const uint4*>(abuf + lane * 128 + (((4 * hh + j) ^ sw) << 4)) : make_uint4(0, 0, 0, 0);
+                else a4 = aux[4 * hh + j];
+                const uint32_t au[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t o[4], g[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x0 = __uint_as_float(r[8 * j + 2 * e]), x1 = __uint_as_float(r[8 * j + 2 * e + 1]);
-                o[e] = pack_bf16(x0, x1);
-                if (EPI == EPI_GELU) {
-                  // GELU of the *rounded* pre-activation so that backward (which only sees bf16 pre) is consistent
-                  float2 xr = unpack_bf16(o[e]);
-                  g[e] = pack_bf16(gelu_tanh(xr.x), gelu_tanh(xr.y));
+                for (int e = 0; e < 4; ++e) {
+                  const float2 av = unpack_bf16(au[e]);
+                  float x0 = __uint_as_float(r[32 * hh + 8 * j + 2 * e]), x1 = __uint_as_float(r[32 * hh + 8 * j + 2 * e + 1]);
+                  if (EPI == EPI_RESIDUAL) { x0 += av.x; x1 += av.y; }
+                  else { x0 *= gelu_tanh_grad(av.x); x1 *= gelu_tanh_grad(av.y); }
+                  o[4 * j + e] = pack_bf16(x0, x1);
                 }
               }
-              *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-              if (EPI == EPI_GELU && valid && col0 + half * 32 + 8 * j < p.N)
-                reinterpret_cast<uint4*>(d2row)[j] = make_uint4(g[0], g[1], g[2], g[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = pack_bf16(__uint_as_float(r[32 * hh + 2 * e]), __uint_as_float(r[32 * hh + 2 * e + 1]));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(rowp + (((4 * hh + j) ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            if (EPI == EPI_GELU) {
+              // GELU of the *rounded* pre-activation so that backward (which only sees bf16 pre) is consistent
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float2 xr = unpack_bf16(o[e]);
+                o[e] = pack_bf16(gelu_tanh(xr.x), gelu_tanh(xr.y));
+              }
+              if (AUXBUF) {                 // second staging box -> TMA store
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(abuf + lane * 128 + (((4 * hh + j) ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              } else {                      // 1-CTA kernel: straight from registers to global memory (one 128-byte line per thread)
+                __nv_bfloat16* d2row = p.d2 + grow * p.ldd2 + col0 + 32 * hh;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (grow < p.M && col0 + 32 * hh + 8 * j < p.N)
+                    reinterpret_cast<uint4*>(d2row)[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              }
             }
           }
+          if (HAS_AUX && AUXBUF) {
+            __syncwarp();                                         // every lane has consumed its operand: the box may be refilled
+            if (c + 2 < BN / 64) request_aux(col0 + 128, row0);   // (the next tile's first box is requested at the top of the loop)
+          }
           fence_proxy_async_smem();
-          named_bar_sync(2, EPI_THREADS);
-          if (issuer) {
-            if (col0 < p.N) {
-              tma_store_2d(&tmD, sbuf, col0, m_blk * BM);
+          __syncwarp();
+          if (lane == 0) {
+            if (col0 < p.N && row0 < p.M) {
+              tma_store_2d(&tmD, sbuf, col0, row0);
+              if (EPI == EPI_GELU && AUXBUF) tma_store_2d(&tmD2, abuf, col0, row0);
             }
             tma_commit_group();
           }
         }
       }
-      // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp (CG2: the leader's, remotely)
-      tc_fence_before();
-      if (CG2) mbar_arrive_cluster(mapa_rank0(smem_u32(&tempty_bar[buf])));
-      else mbar_arrive(&tempty_bar[buf]);
     }
-    if (issuer) tma_wait_group<0>();
+    if (lane == 0) tma_wait_group<0>();
   }
 
   tc_fence_before();
@@ -602,10 +665,16 @@ static bool use_cg2() {
   return g_use_cg2 == 1;
 }
 
-template <bool A_MN, bool B_MN, int EPI, bool FP8 = false>
+// MIDGPT_GEMM_AUXBUF = 0 | 1 forces the register / TMA-box path of the epilogue's second operand; default: boxes iff K <= 1024
+static bool use_auxbuf(int K) {
+  static const int mode = [] { const char* e = getenv("MIDGPT_GEMM_AUXBUF"); return e ? atoi(e) : -1; }();
+  return mode < 0 ? K <= 1024 : mode != 0;
+}
+
+template <bool A_MN, bool B_MN, int EPI, bool FP8 = false, bool AUXB = false>
 static void launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tD2,
                         const GemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, false, FP8, true>;
+  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, false, FP8, true, AUXB>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -680,8 +749,10 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
                     int epi, int accumulate, int num_sms, cudaStream_t stream, const GatherParams* ag) {
   CUtensorMap tA = a_mn ? make_tmap_2d(a, 2, K, M, lda, 64, BK) : make_tmap_2d(a, 2, M, K, lda, BK, BM);
   CUtensorMap tB = b_mn ? make_tmap_2d(b, 2, K, N, ldb, 64, BK) : make_tmap_2d(b, 2, N, K, ldb, BK, BN);
-  CUtensorMap tD = (epi == EPI_F32) ? make_tmap_2d(d, 4, M, N, ldd, 32, BM) : make_tmap_2d(d, 2, M, N, ldd, 64, BM);
-  CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
+  CUtensorMap tD = (epi == EPI_F32) ? make_tmap_2d(d, 4, M, N, ldd, 32, 32) : make_tmap_2d(d, 2, M, N, ldd, 64, 32);   // one box per epilogue warp
+  // second [M, N] bf16 tile of the epilogue: gelu output (stored) or residual / pre-activation operand (loaded); pair kernels only
+  CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, 32)
+                    : ((epi == EPI_RESIDUAL || epi == EPI_DGELU) ? make_tmap_2d(aux, 2, M, N, ld_aux, 64, 32) : tD);
   GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, pick_group_m(N, num_sms), 1, static_cast<__nv_bfloat16*>(d2), ldd2, nullptr, nullptr};
   if (ag) {
     p.ag = *ag;
@@ -701,19 +772,27 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
     CUtensorMap tB2 = b_mn ? tB : make_tmap_2d(b, 2, N, K, ldb, BK, BN / 2);
     p.group_m = pick_group_m(N, num_sms / 2);
     p.split_k = pick_split_k(((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN), num_sms / 2, (K + BK - 1) / BK, epi, accumulate);
+    // second [M, N] tile of the epilogue through TMA boxes (5 operand stages) or through registers (6 stages): the boxes win
+    // when the k-loop is short and the epilogue sets the pace (K = 768), the deeper ring when it is long
+    const bool auxb = use_auxbuf(K);
 #define MG_PAIR(AM, BM_, E) \
     if (a_mn == AM && b_mn == BM_ && epi == E) return launch_pair<AM, BM_, E>(tA, tB2, tD, tD2, p, num_sms, stream);
+#define MG_PAIRX(AM, BM_, E) \
+    if (a_mn == AM && b_mn == BM_ && epi == E) { \
+      if (auxb) return launch_pair<AM, BM_, E, false, true>(tA, tB2, tD, tD2, p, num_sms, stream); \
+      return launch_pair<AM, BM_, E>(tA, tB2, tD, tD2, p, num_sms, stream); }
     MG_PAIR(false, false, EPI_STORE)
-    MG_PAIR(false, false, EPI_RESIDUAL)
-    MG_PAIR(false, false, EPI_GELU)
+    MG_PAIRX(false, false, EPI_RESIDUAL)
+    MG_PAIRX(false, false, EPI_GELU)
     MG_PAIR(false, false, EPI_F32)
     MG_PAIR(false, true, EPI_STORE)
-    MG_PAIR(false, true, EPI_DGELU)
-    MG_PAIR(false, true, EPI_RESIDUAL)
+    MG_PAIRX(false, true, EPI_DGELU)
+    MG_PAIRX(false, true, EPI_RESIDUAL)
     MG_PAIR(true, true, EPI_F32)
     MG_PAIR(true, true, EPI_STORE)
     MG_PAIR(true, false, EPI_F32)
 #undef MG_PAIR
+#undef MG_PAIRX
   }
   p.split_k = pick_split_k(((M + BM - 1) / BM) * ((N + BN - 1) / BN), num_sms, (K + BK - 1) / BK, epi, accumulate);
 #define MG_CASE(AM, BM_, E) \
@@ -738,8 +817,9 @@ void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb,
                      cudaStream_t stream) {
   CUtensorMap tA = make_tmap_2d(a, 1, M, K, lda, 2 * BK, BM);
   CUtensorMap tB = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN);
-  CUtensorMap tD = make_tmap_2d(d, 2, M, N, ldd, 64, BM);
-  CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, BM) : tD;
+  CUtensorMap tD = make_tmap_2d(d, 2, M, N, ldd, 64, 32);
+  CUtensorMap tD2 = (epi == EPI_GELU) ? make_tmap_2d(d2, 2, M, N, ldd2, 64, 32)
+                    : (epi == EPI_RESIDUAL ? make_tmap_2d(aux, 2, M, N, ld_aux, 64, 32) : tD);
   GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, 0, GatherParams{}, pick_group_m(N, num_sms), 1, static_cast<__nv_bfloat16*>(d2), ldd2, sa, sb};
   if (use_cg2() && M >= 2 * BM) {
     CUtensorMap tB2 = make_tmap_2d(b, 1, N, K, ldb, 2 * BK, BN / 2);

@@ -192,24 +192,18 @@ class B200Backend:
         qk = h.qk.view(B, T, 2, H, C)
         return qk[:, :, 0], qk[:, :, 1], h.raw.view(B, T, 3, H, C)[:, :, 2]
 
-    def _packed(self, h: QKV, B, T, H, C):
-        D = H * C
-        return torch.cat((h.qk, h.raw[:, 2 * D:]), dim=1)
-
     def attention_fwd(self, h: QKV, B, T, H, C, dropout_p=0.0, seed=0):
-        if dropout_p > 0.0:   # attention-prob dropout is only used by the 10 M-parameter char model
-            return self._torch.attention_fwd(self._packed(h, B, T, H, C), B, T, H, C, dropout_p, seed)
+        """Causal flash attention; ``dropout_p`` > 0 drops attention probabilities *inside* the kernel (reference
+        src/model.py:78): a Philox keep-mask keyed by ``seed`` is applied to P in registers after the row sum."""
         q, k, v = self._views(h, B, T, H, C)
         self.launches += 1
-        o, lse = self.ext.attn_fwd(q, k, v)
+        o, lse = self.ext.attn_fwd(q, k, v, float(dropout_p), int(seed) & 0x7FFFFFFFFFFFFFFF)
         return o, lse
 
     def attention_bwd(self, do, h: QKV, o, lse, B, T, H, C, dropout_p=0.0, seed=0):
-        if dropout_p > 0.0:
-            return self._torch.attention_bwd(do, self._packed(h, B, T, H, C), o, lse, B, T, H, C, dropout_p, seed)
         q, k, v = self._views(h, B, T, H, C)
         self.launches += 3
-        return self.ext.attn_bwd(q, k, v, o, do.contiguous(), lse)
+        return self.ext.attn_bwd(q, k, v, o, do.contiguous(), lse, float(dropout_p), int(seed) & 0x7FFFFFFFFFFFFFFF)
 
     # ---------------------------------------------------------------- LM head + cross-entropy
     def _logits_buf(self, rows: int, vpad: int) -> torch.Tensor:
