@@ -121,8 +121,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = bars + 9;        // 2 (one per S buffer)
   uint64_t* p_full = bars + 11;       // 2 (128 arrivals each; one per S/P buffer -- a softmax warp may run a tile ahead of the others, and its
                                       //    arrival for tile j+1 must not be counted towards tile j: tile j+2 cannot start before p_full(j) completed)
-  uint64_t* pv_done = bars + 13;      // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* pv_done = bars + 13;      // 1: completes once per P·V (awaited LAZILY: only when a row maximum forces a rescale of O)
+  uint64_t* o_done = bars + 14;       // 1: the LAST P·V has retired.  The epilogue must not use a parity wait on pv_done: a warp that
+                                      //    never rescaled has skipped phases, and if it runs two tiles ahead of the slowest warp the
+                                      //    phase it asks for aliases one that completed long ago (it then normalises an O that lacks the
+                                      //    last two key tiles -- an intermittent few-percent error on 32 rows, caught by the row-wise test)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;          // heavy (late) query tiles first
@@ -134,7 +138,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&p_full[0], 128); mbar_init(&p_full[1], 128); mbar_init(pv_done, 1);
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&p_full[0], 128); mbar_init(&p_full[1], 128); mbar_init(pv_done, 1); mbar_init(o_done, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -204,6 +208,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_bf16_ts(tmem + Cfg::O_COL, tmem + Cfg::S_COL + st * BKV + k * 8, desc_shift(v_desc, k * 2048), idesc_o, (j | k) != 0);
           umma_commit(&v_empty[st]);
           umma_commit(pv_done);
+          if (j + 1 == n_kv) umma_commit(o_done);
         }
         __syncwarp();
         if (j + 2 < n_kv) issue_qk(j + 2);   // reuses S buffer j&1, which the softmax warps released at p_full(j)
@@ -324,7 +329,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive(&p_full[j & 1]);
     }
     // epilogue: O / l -> bf16 -> global ; lse
-    mbar_wait(pv_done, (n_kv - 1) & 1);
+    mbar_wait(o_done, 0);
     tc_fence_after();
     const float inv_l = 1.f / l;
     const bool valid = q_idx < T;

@@ -9,10 +9,10 @@ std::vector<int> gemm_work_plan(int M, int N, int K, int epi, int accumulate, in
 void gemm_launch(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d, long long ldd,
                  void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int accumulate,
                  int num_sms, cudaStream_t stream);
-void gemm_launch_ag_raw(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, void* d2, long long ldd2,
-                        const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms, cudaStream_t stream,
-                        const long long* peer_ptrs, void* local, unsigned int* flags, long long chunk_elems, long long b_offset,
-                        unsigned int target, int world, int rank, int n_ctas);
+void gemm_launch_ag_raw(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d, long long ldd, void* d2,
+                        long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int accumulate, int num_sms,
+                        cudaStream_t stream, const long long* peer_ptrs, void* local, unsigned int* flags, long long chunk_elems,
+                        unsigned int target, int world, int rank);
 void gemm_fp8_launch(const void* a, long long lda, const void* b, long long ldb, const float* sa, const float* sb, void* d, long long ldd,
                      void* d2, long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms,
                      cudaStream_t stream);
@@ -63,9 +63,17 @@ cudaStream_t stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 #define CHECK_F32(t) TORCH_CHECK((t).is_cuda() && (t).scalar_type() == at::kFloat, #t " must be a CUDA fp32 tensor")
 #define CHECK_2D_ROWMAJOR(t) TORCH_CHECK((t).dim() == 2 && (t).stride(1) == 1, #t " must be 2-D with unit inner stride")
 
-// d (+)= op(a) · op(b)ᵀ ; see csrc/gemm.cu for operand conventions.
-void gemm(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn, at::Tensor& d, int64_t epi,
-          const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& aux, bool accumulate) {
+// d (+)= op(a) · op(b)ᵀ ; see csrc/gemm.cu for operand conventions.  With `gather` the same GEMM also carries the all-gather of an
+// FSDP unit (all-gather ⊕ GEMM): the remote chunks of `local` are pulled from the owners' symmetric shards by copy warps inside
+// the GEMM's own CTAs; if b is a view into `local` the kernel synchronises with them per 64 KB segment.
+struct GatherArgs {
+  std::vector<long long> peers;
+  at::Tensor local, flags;
+  int64_t chunk_elems, target, rank;
+};
+
+static void gemm_impl(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn, at::Tensor& d, int64_t epi,
+                      const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& aux, bool accumulate, const GatherArgs* ga) {
   c10::cuda::CUDAGuard guard(a.device());
   CHECK_BF16(a); CHECK_BF16(b); CHECK_2D_ROWMAJOR(a); CHECK_2D_ROWMAJOR(b); CHECK_2D_ROWMAJOR(d);
   const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
@@ -91,34 +99,35 @@ void gemm(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn, at::Te
     TORCH_CHECK(d2->size(0) == M && d2->size(1) == N);
     d2p = d2->data_ptr(); ldd2 = d2->stride(0);
   }
-  mg::gemm_launch(a.data_ptr(), a.stride(0), a_mn, b.data_ptr(), b.stride(0), b_mn, d.data_ptr(), d.stride(0), d2p, ldd2, auxp,
-                  ld_aux, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), accumulate ? 1 : 0,
-                  num_sms_of(a), stream());
+  if (ga == nullptr) {
+    mg::gemm_launch(a.data_ptr(), a.stride(0), a_mn, b.data_ptr(), b.stride(0), b_mn, d.data_ptr(), d.stride(0), d2p, ldd2, auxp,
+                    ld_aux, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), accumulate ? 1 : 0,
+                    num_sms_of(a), stream());
+    return;
+  }
+  CHECK_BF16(ga->local);
+  const int64_t world = static_cast<int64_t>(ga->peers.size());
+  TORCH_CHECK(ga->local.is_contiguous() && ga->flags.scalar_type() == at::kInt && ga->flags.is_contiguous());
+  TORCH_CHECK(ga->chunk_elems % 8 == 0 && world * ga->chunk_elems <= ga->local.numel(), "gemm_ag: unit buffer too small");
+  TORCH_CHECK(ga->flags.numel() >= (world * ga->chunk_elems + 32767) / 32768 + 16,
+              "gemm_ag: flags needs one word per 32768-element segment (+16 for the stand-alone pull)");
+  mg::gemm_launch_ag_raw(a.data_ptr(), a.stride(0), a_mn, b.data_ptr(), b.stride(0), b_mn, d.data_ptr(), d.stride(0), d2p, ldd2, auxp,
+                         ld_aux, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), accumulate ? 1 : 0,
+                         num_sms_of(a), stream(), ga->peers.data(), ga->local.data_ptr(),
+                         reinterpret_cast<unsigned int*>(ga->flags.data_ptr()), ga->chunk_elems, static_cast<unsigned int>(ga->target),
+                         static_cast<int>(world), static_cast<int>(ga->rank));
 }
 
-// all-gather ⊕ GEMM: d = a · bᵀ where b ([N,K], K-major) is a sub-range of the local gathered unit buffer `local`, whose
-// remote chunks are pulled from `peer_ptrs` by the first n_ctas CTAs of the same kernel (csrc/gemm.cu).
-void gemm_ag(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, int64_t epi, const c10::optional<at::Tensor>& d2,
-             const c10::optional<at::Tensor>& aux, std::vector<int64_t> peer_ptrs, at::Tensor& local, at::Tensor& flags,
-             int64_t chunk_elems, int64_t target, int64_t rank, int64_t n_ctas) {
-  c10::cuda::CUDAGuard guard(a.device());
-  CHECK_BF16(a); CHECK_BF16(b); CHECK_BF16(d); CHECK_BF16(local); CHECK_2D_ROWMAJOR(a); CHECK_2D_ROWMAJOR(b); CHECK_2D_ROWMAJOR(d);
-  TORCH_CHECK(b.is_contiguous() && local.is_contiguous() && flags.scalar_type() == at::kInt);
-  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
-  TORCH_CHECK(b.size(1) == K && d.size(0) == M && d.size(1) == N);
-  const int64_t b_offset = (reinterpret_cast<const char*>(b.data_ptr()) - reinterpret_cast<const char*>(local.data_ptr())) / 2;
-  TORCH_CHECK(b_offset >= 0 && b_offset + N * K <= local.numel(), "gemm_ag: b must live inside the local unit buffer");
-  TORCH_CHECK(chunk_elems % 8 == 0 && static_cast<int64_t>(peer_ptrs.size()) * chunk_elems <= local.numel());
-  TORCH_CHECK(flags.numel() >= (static_cast<int64_t>(peer_ptrs.size()) * chunk_elems + 32767) / 32768, "gemm_ag: flags needs one word per 32768-element segment");
-  const void* auxp = nullptr; long long ld_aux = 0;
-  if (epi == 1 || epi == 3) { TORCH_CHECK(aux.has_value()); CHECK_BF16(*aux); auxp = aux->data_ptr(); ld_aux = aux->stride(0); }
-  void* d2p = nullptr; long long ldd2 = 0;
-  if (epi == 2) { TORCH_CHECK(d2.has_value()); CHECK_BF16(*d2); d2p = d2->data_ptr(); ldd2 = d2->stride(0); }
-  std::vector<long long> pp(peer_ptrs.begin(), peer_ptrs.end());
-  mg::gemm_launch_ag_raw(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), d.data_ptr(), d.stride(0), d2p, ldd2, auxp, ld_aux,
-                         static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), static_cast<int>(epi), num_sms_of(a), stream(),
-                         pp.data(), local.data_ptr(), reinterpret_cast<unsigned int*>(flags.data_ptr()), chunk_elems, b_offset,
-                         static_cast<unsigned int>(target), static_cast<int>(pp.size()), static_cast<int>(rank), static_cast<int>(n_ctas));
+void gemm(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn, at::Tensor& d, int64_t epi,
+          const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& aux, bool accumulate) {
+  gemm_impl(a, a_mn, b, b_mn, d, epi, d2, aux, accumulate, nullptr);
+}
+
+void gemm_ag(const at::Tensor& a, bool a_mn, const at::Tensor& b, bool b_mn, at::Tensor& d, int64_t epi,
+             const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& aux, bool accumulate,
+             std::vector<int64_t> peer_ptrs, at::Tensor& local, at::Tensor& flags, int64_t chunk_elems, int64_t target, int64_t rank) {
+  GatherArgs ga{std::vector<long long>(peer_ptrs.begin(), peer_ptrs.end()), local, flags, chunk_elems, target, rank};
+  gemm_impl(a, a_mn, b, b_mn, d, epi, d2, aux, accumulate, &ga);
 }
 
 // row-wise e4m3 quantisation: returns (q uint8 [R,C], dequant fp32 [R])
@@ -336,7 +345,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM with fused epilogues");
   m.def("gemm_work_plan", [](int M, int N, int K, int epi, int accumulate, int num_sms, bool pairs) { return mg::gemm_work_plan(M, N, K, epi, accumulate, num_sms, pairs); },
         "host replay of the GEMM tile / K-slice schedule: flat list of (worker, tile, kb0, kb1)");
-  m.def("gemm_ag", &gemm_ag, "all-gather (NVLink pull) fused with the tcgen05 GEMM");
+  m.def("gemm_ag", &gemm_ag, "tcgen05 GEMM that carries the NVLink all-gather of an FSDP unit (copy warps in every CTA)");
   m.def("quant_rows_e4m3", &quant_rows_e4m3);
   m.def("quant_mx_e4m3", &quant_mx_e4m3);
   m.def("gemm_mx", &gemm_mx, "MXFP8 block-scaled GEMM (tcgen05 kind::mxf8f6f4.block_scale)");

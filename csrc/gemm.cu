@@ -44,20 +44,29 @@ enum Epilogue : int {
   EPI_F32 = 4,        // D (+)= acc                    (fp32; accumulate via TMA reduce-add)
 };
 
-// Optional fused all-gather (all-gather ⊕ GEMM): the B operand lives inside a flat FSDP unit
-// buffer whose world equal chunks are owned by different ranks.  The first `n_ctas` CTAs first PULL the peers'
-// chunks over NVLink into the local buffer and publish one ready flag per chunk; every CTA's TMA producer polls
-// the flags of the chunks its B tile touches, and tiles are visited so that locally-owned rows come first.
+// Fused all-gather (all-gather ⊕ GEMM).  The weights of an FSDP unit live in a flat buffer whose `world` equal
+// chunks are owned by different ranks.  A pair-kernel GEMM can CARRY the gather of a whole unit: two extra warps in EVERY CTA
+// (64 threads x 16 outstanding 16-byte NVLink loads = 16 KB in flight per SM, 2.4 MB per GPU -- what the stand-alone pull needs
+// for ~570 GB/s) pull the remote 64 KB segments of the unit from the owners' symmetric shards into the local buffer, in address
+// order starting at the carrier's own B operand, and publish one release-flag per segment.  No SM is taken away from the GEMM
+// (round 1 dedicated ~24 copy-engine CTAs and lost both their tiles and, at 24 x 320 threads, most of the link bandwidth).
+// If the carrier's B operand is itself part of the unit (forward QKV / MLP-in / LM-head GEMM: K-major rows; dgrad: MN-major
+// k-rows) its TMA producers acquire the flags of the segments below the rows they are about to load (a watermark: segments
+// land in address order and every CTA's tiles ascend through B).  Later kernels of the stream need no flags at all: the carrier
+// does not retire before its copy warps have finished.
 struct GatherParams {
   void* peer[8];                    // peer[c] = rank c's bf16 shard (symmetric memory), length chunk_elems
   __nv_bfloat16* local;             // local gathered unit buffer, world * chunk_elems elements
   unsigned int* flags;              // one word per SEG_ELEMS-element segment of the unit; == target (epoch) once the segment landed
   long long chunk_elems;            // elements per chunk (multiple of 8)
-  long long b_offset;               // element offset of the B matrix inside the unit buffer
+  long long b_offset;               // element offset of this GEMM's B matrix inside the unit buffer; < 0: B is not in the unit (no polling)
+  long long first_seg;              // the pull starts at this segment (the carrier's own B) and wraps around
   unsigned int target;              // epoch of this call (monotonically increasing per flags buffer)
-  int world, rank, n_ctas;
+  int world, rank;
+  int n_seg;                        // segments of the unit; 0 = this GEMM carries no gather
 };
 constexpr long long SEG_ELEMS = 32768;   // 64 KB of bf16: flag granularity of the fused gather (a 256-row weight tile at K=2048 is 16 segments)
+constexpr int COPY_THREADS = 64;         // two copy warps per CTA (pair kernels only)
 
 struct GemmParams {
   const __nv_bfloat16* aux;
@@ -118,7 +127,7 @@ struct WorkIter {
 };
 
 template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false, bool CG2 = false, bool AUXB = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(CG2 ? NUM_THREADS + COPY_THREADS : NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                   const GemmParams p) {
@@ -178,93 +187,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- fused all-gather: the first n_ctas CTAs are in-kernel NVLink copy engines publishing one flag per 64 KB segment;
-  // the remaining CTAs run the GEMM and their TMA producers poll the flags of the segments their weight tile covers.
-  const bool gather = AG && p.ag.n_ctas > 0;      // compile-time off for the plain kernels: zero cost on the common path
-  if (gather && static_cast<int>(blockIdx.x) < p.ag.n_ctas) {
-    // Copy-engine CTA: all 320 threads pull 64 KB segments with 13 independent 16-byte NVLink loads in flight per thread
-    // (measured on B200: 546 GB/s with 32 such CTAs vs 426 GB/s for single-thread cp.async.bulk rings, profiles/comm_bench_*).
-    // Segments are visited in address order, interleaved over the copy-engine CTAs, so the weight matrix this GEMM multiplies
-    // lands first; one release-store per segment publishes it to the TMA producers of the GEMM CTAs.
-    const long long unit_elems = p.ag.chunk_elems * p.ag.world;
-    const long long n_seg = (unit_elems + SEG_ELEMS - 1) / SEG_ELEMS;
-    const long long loc0 = static_cast<long long>(p.ag.rank) * p.ag.chunk_elems, loc1 = loc0 + p.ag.chunk_elems;
-    constexpr int V16 = static_cast<int>(SEG_ELEMS / 8);                  // uint4 per segment (4096)
-    constexpr int PER_T = (V16 + NUM_THREADS - 1) / NUM_THREADS;          // 13
-    // Two segments per round: 26 independent 16-byte peer loads in flight per thread (128 KB per CTA), then the stores, one
-    // fence + barrier, and the two release-flags.
-    auto seg_remote = [&](long long seg) {
-      const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
-      return seg < n_seg && !(e0 >= loc0 && e1 <= loc1);
-    };
-    auto load_seg = [&](long long seg, uint4 (&v)[PER_T], uint32_t& live) {
-      const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
-      // one 64-bit division per segment (not per load): a 64 KB segment touches at most two chunks
-      const int c0 = static_cast<int>(e0 / p.ag.chunk_elems);
-      const long long c0_end = static_cast<long long>(c0 + 1) * p.ag.chunk_elems;
-      const __nv_bfloat16* base0 = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c0]) - static_cast<long long>(c0) * p.ag.chunk_elems;
-      const int c1 = c0 + 1 < p.ag.world ? c0 + 1 : c0;
-      const __nv_bfloat16* base1 = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c1]) - static_cast<long long>(c1) * p.ag.chunk_elems;
-      live = 0;
-#pragma unroll
-      for (int u = 0; u < PER_T; ++u) {
-        const long long e = e0 + (static_cast<long long>(u) * NUM_THREADS + threadIdx.x) * 8;
-        if (e < e1) {
-          bool second = e >= c0_end;
-          int c = second ? c1 : c0;
-          const __nv_bfloat16* base = second ? base1 : base0;
-          if (p.ag.chunk_elems < SEG_ELEMS) {        // tiny unit (e.g. a 65-token LM head): a segment may span > 2 chunks — exact, slow path
-            c = static_cast<int>(e / p.ag.chunk_elems);
-            base = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c]) - static_cast<long long>(c) * p.ag.chunk_elems;
-          }
-          if (c != p.ag.rank) {
-            const uint4* src = reinterpret_cast<const uint4*>(base + e);
-            asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src));
-            live |= 1u << u;
-          }
-        }
-      }
-    };
-    auto store_seg = [&](long long seg, const uint4 (&v)[PER_T], uint32_t live) {
-      const long long e0 = seg * SEG_ELEMS;
-#pragma unroll
-      for (int u = 0; u < PER_T; ++u)
-        if (live & (1u << u)) *reinterpret_cast<uint4*>(p.ag.local + e0 + (static_cast<long long>(u) * NUM_THREADS + threadIdx.x) * 8) = v[u];
-    };
-    // One fence + barrier per ROUNDS rounds (8 segments): the block-wide fence costs several microseconds, the copies do not.
-    constexpr int ROUNDS = 4;
-    long long pend[2 * ROUNDS];
-    for (long long seg0 = blockIdx.x; seg0 < n_seg; seg0 += 2LL * ROUNDS * p.ag.n_ctas) {
-      int n_pend = 0;
-#pragma unroll 1
-      for (int rd = 0; rd < ROUNDS; ++rd) {
-        const long long sa = seg0 + 2LL * rd * p.ag.n_ctas, sb = sa + p.ag.n_ctas;
-        const bool ra = seg_remote(sa), rb = seg_remote(sb);
-        if (!ra && !rb) continue;
-        uint4 va[PER_T], vb[PER_T];
-        uint32_t la = 0, lb = 0;
-        if (ra) load_seg(sa, va, la);
-        if (rb) load_seg(sb, vb, lb);
-        if (ra) { store_seg(sa, va, la); pend[n_pend++] = sa; }
-        if (rb) { store_seg(sb, vb, lb); pend[n_pend++] = sb; }
-      }
-      if (n_pend == 0) continue;
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        asm volatile("fence.proxy.async.global;" ::: "memory");           // consumed by TMA (async proxy) in the GEMM CTAs
-        for (int i = 0; i < n_pend; ++i)
-          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + pend[i]), "r"(p.ag.target) : "memory");
-      }
-    }
-    // copy-engine CTAs own no GEMM tiles: fall through to the common teardown
-  }
-  const int n_pull = gather ? p.ag.n_ctas : 0;
-  const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x) - n_pull;   // negative for copy-engine CTAs
-  const int tile_stride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x) - n_pull;
+  const bool carry = CG2 && p.ag.n_seg > 0;               // this launch carries the gather of an FSDP unit (copy warps 10-11)
+  const bool poll = carry && p.ag.b_offset >= 0;           // ... and its own B operand is part of that unit
+  const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_stride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-  // tile -> (m_blk, n_blk).  With a fused gather the n-blocks are rotated so that locally-owned weight rows come first.
-  const int n_rot = 0;   // segments land in address order, i.e. ascending weight rows: visit n-blocks in natural order
+  // tile -> (m_blk, n_blk)
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
     const int per_group = p.group_m * num_n;
     const int g = tile / per_group;
@@ -273,10 +201,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int r = tile - g * per_group;
     m_blk = first_m + r % gsize;
     n_blk = r / gsize;
-    if (gather) {
-      int rot = n_rot < 0 ? 0 : (n_rot >= num_n ? 0 : n_rot);
-      n_blk = (n_blk + rot) % num_n;
-    }
     if (CG2) m_blk = 2 * m_blk + static_cast<int>(cta_rank);      // this CTA's 128-row block inside the pair's 256-row tile
   };
 
@@ -285,24 +209,32 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // fused gather: every segment below `watermark` is known to have landed (segments arrive in address order starting at
+      // this GEMM's B, and this CTA's tiles / k-blocks ascend through B, so each flag is acquired at most once per CTA)
+      long long watermark = poll ? p.ag.b_offset / SEG_ELEMS : 0;
+      auto acquire_upto = [&](long long e_end) {
+        if (watermark * SEG_ELEMS >= e_end) return;
+        const long long loc0 = static_cast<long long>(p.ag.rank) * p.ag.chunk_elems, loc1 = loc0 + p.ag.chunk_elems;
+        while (watermark * SEG_ELEMS < e_end) {
+          const long long s0 = watermark * SEG_ELEMS, s1 = s0 + SEG_ELEMS;
+          if (!(s0 >= loc0 && s1 <= loc1))                    // (locally owned segments are in place before the launch)
+            while (static_cast<int>(ld_acquire_gpu_u32(p.ag.flags + watermark) - p.ag.target) < 0) {
+            }
+          ++watermark;
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // the copy warps' generic-proxy stores -> this thread's TMA loads
+      };
       WorkIter work(tile0, tile_stride, tiles_mn, num_k_total, p.split_k);
       for (int tile, kb0, kb1; work.next(tile, kb0, kb1);) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
-        if (gather) {
-          const long long e0 = p.ag.b_offset + static_cast<long long>(n_blk) * BN * p.K;
-          const long long rows = min(BN, p.N - n_blk * BN);
-          const long long e1 = e0 + rows * p.K;
-          const long long loc0 = static_cast<long long>(p.ag.rank) * p.ag.chunk_elems, loc1 = loc0 + p.ag.chunk_elems;
-          for (long long sgm = e0 / SEG_ELEMS; sgm * SEG_ELEMS < e1; ++sgm) {
-            const long long s0 = sgm * SEG_ELEMS, s1 = s0 + SEG_ELEMS;
-            if (s0 >= loc0 && s1 <= loc1) continue;                 // locally owned rows
-            while (static_cast<int>(ld_acquire_gpu_u32(p.ag.flags + sgm) - p.ag.target) < 0) {
-            }
-          }
-          asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (poll && !B_MN) {       // K-major B: rows [.., b_row_end) of the weight, whole rows
+          const int b_row_end = min(p.N, n_blk * BN + (static_cast<int>(cta_rank) + 1) * (BN / 2));
+          acquire_upto(p.ag.b_offset + static_cast<long long>(b_row_end) * p.K);
         }
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (poll && B_MN)          // MN-major B (dgrad): k-rows [.., (kb+1)*BK) of the weight, whole rows of N elements
+            acquire_upto(p.ag.b_offset + static_cast<long long>(min(p.K, (kb + 1) * BK)) * p.N);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * STG;
           uint8_t* sB = sA + A_STAGE_BYTES;
@@ -388,6 +320,60 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 2 + EPI_THREADS / 32) {
+    // ===================== copy warps (pair kernels): the all-gather this GEMM carries =====================
+    if (carry) {
+      const int tid = static_cast<int>(threadIdx.x) - NUM_THREADS;          // 0..63
+      const long long unit_elems = p.ag.chunk_elems * p.ag.world;
+      const long long loc0 = static_cast<long long>(p.ag.rank) * p.ag.chunk_elems, loc1 = loc0 + p.ag.chunk_elems;
+      constexpr int PER_RD = 16;                                            // 16 x 16 B in flight per thread
+      constexpr int ROUNDS = static_cast<int>(SEG_ELEMS / 8) / (COPY_THREADS * PER_RD);   // 4
+      for (long long i = blockIdx.x; i < p.ag.n_seg; i += gridDim.x) {
+        long long seg = p.ag.first_seg + i;
+        if (seg >= p.ag.n_seg) seg -= p.ag.n_seg;
+        const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
+        if (e0 >= loc0 && e1 <= loc1) continue;                              // owned by this rank: already in place
+        // one 64-bit division per segment: a 64 KB segment touches at most two chunks (unless the unit is tiny)
+        const int c0 = static_cast<int>(e0 / p.ag.chunk_elems);
+        const long long c0_end = static_cast<long long>(c0 + 1) * p.ag.chunk_elems;
+        const int c1 = c0 + 1 < p.ag.world ? c0 + 1 : c0;
+        const __nv_bfloat16* base0 = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c0]) - static_cast<long long>(c0) * p.ag.chunk_elems;
+        const __nv_bfloat16* base1 = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c1]) - static_cast<long long>(c1) * p.ag.chunk_elems;
+#pragma unroll 1
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+          uint4 v[PER_RD];
+          uint32_t live = 0;
+#pragma unroll
+          for (int u = 0; u < PER_RD; ++u) {
+            const long long e = e0 + (static_cast<long long>(rd * PER_RD + u) * COPY_THREADS + tid) * 8;
+            if (e < e1) {
+              const bool second = e >= c0_end;
+              int c = second ? c1 : c0;
+              const __nv_bfloat16* base = second ? base1 : base0;
+              if (p.ag.chunk_elems < SEG_ELEMS) {      // tiny unit: a segment may span more than two chunks -- exact, slow path
+                c = static_cast<int>(e / p.ag.chunk_elems);
+                base = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c]) - static_cast<long long>(c) * p.ag.chunk_elems;
+              }
+              if (c != p.ag.rank) {
+                const uint4* src = reinterpret_cast<const uint4*>(base + e);
+                asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src));
+                live |= 1u << u;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < PER_RD; ++u)
+            if (live & (1u << u))
+              *reinterpret_cast<uint4*>(p.ag.local + e0 + (static_cast<long long>(rd * PER_RD + u) * COPY_THREADS + tid) * 8) = v[u];
+        }
+        __threadfence();
+        named_bar_sync(3, COPY_THREADS);
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.global;" ::: "memory");           // consumed by TMA (async proxy)
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + seg), "r"(p.ag.target) : "memory");
         }
       }
     }
@@ -683,10 +669,10 @@ static void launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUte
   }
   const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
   int pairs = num_sms / 2;
-  if (num_tiles * (p.split_k > 0 ? p.split_k : 1) < pairs) pairs = num_tiles * (p.split_k > 0 ? p.split_k : 1);
+  if (num_tiles * (p.split_k > 0 ? p.split_k : 1) < pairs && p.ag.n_seg == 0) pairs = num_tiles * (p.split_k > 0 ? p.split_k : 1);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.gridDim = dim3(2 * pairs);                       // (a carried gather keeps every SM's copy warps: idle pairs own no tiles)
+  cfg.blockDim = dim3(NUM_THREADS + COPY_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -709,10 +695,6 @@ static void launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   int grid = num_tiles * (p.split_k > 0 ? p.split_k : 1) < num_sms ? num_tiles * (p.split_k > 0 ? p.split_k : 1) : num_sms;
-  if (AG && p.ag.n_ctas > 0) {                      // copy-engine CTAs come on top of the GEMM workers (all co-resident: 1 CTA / SM)
-    const int workers = num_tiles < num_sms - p.ag.n_ctas ? num_tiles : num_sms - p.ag.n_ctas;
-    grid = workers + p.ag.n_ctas;
-  }
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tA, tB, tD, tD2, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("gemm launch: ") + cudaGetErrorString(e));
@@ -730,18 +712,31 @@ void gemm_launch(const void* a, long long lda, bool a_mn, const void* b, long lo
   gemm_launch_ag(a, lda, a_mn, b, ldb, b_mn, d, ldd, d2, ldd2, aux, ld_aux, M, N, K, epi, accumulate, num_sms, stream, nullptr);
 }
 
-// Host entry for all-gather ⊕ GEMM: same as gemm_launch plus the gather description (b must be K-major and be the
-// sub-range [b_offset, b_offset + N*K) of the local unit buffer).
-void gemm_launch_ag_raw(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, void* d2, long long ldd2,
-                        const void* aux, long long ld_aux, int M, int N, int K, int epi, int num_sms, cudaStream_t stream,
-                        const long long* peer_ptrs, void* local, unsigned int* flags, long long chunk_elems, long long b_offset,
-                        unsigned int target, int world, int rank, int n_ctas) {
+void ag_pull(const long long* lp_ptrs, void* local, long long shard_elems, int rank, int world, unsigned* flags, int n_ctas, cudaStream_t s);
+
+// Host entry for all-gather ⊕ GEMM: any GEMM plus the description of the FSDP unit whose gather it carries.  If b lies inside the
+// unit buffer (a weight of this very unit) the kernel's TMA producers synchronise with the copy warps segment by segment and the
+// pull starts at b; otherwise the GEMM just hides the pull.  GEMMs that cannot take the pair kernel (M < 256) fall back to the
+// stand-alone NVLink pull kernel followed by the plain GEMM.
+void gemm_launch_ag_raw(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d, long long ldd, void* d2,
+                        long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int accumulate, int num_sms,
+                        cudaStream_t stream, const long long* peer_ptrs, void* local, unsigned int* flags, long long chunk_elems,
+                        unsigned int target, int world, int rank) {
+  if (!(use_cg2() && M >= 2 * BM)) {
+    ag_pull(peer_ptrs, local, chunk_elems, rank, world, flags + (chunk_elems * world + SEG_ELEMS - 1) / SEG_ELEMS, 32, stream);
+    return gemm_launch_ag(a, lda, a_mn, b, ldb, b_mn, d, ldd, d2, ldd2, aux, ld_aux, M, N, K, epi, accumulate, num_sms, stream, nullptr);
+  }
   GatherParams ag{};
   for (int i = 0; i < 8; ++i) ag.peer[i] = i < world ? reinterpret_cast<void*>(peer_ptrs[i]) : nullptr;
   ag.local = static_cast<__nv_bfloat16*>(local);
-  ag.flags = flags; ag.chunk_elems = chunk_elems; ag.b_offset = b_offset; ag.target = target;
-  ag.world = world; ag.rank = rank; ag.n_ctas = n_ctas;
-  gemm_launch_ag(a, lda, false, b, ldb, false, d, ldd, d2, ldd2, aux, ld_aux, M, N, K, epi, 0, num_sms, stream, &ag);
+  ag.flags = flags; ag.chunk_elems = chunk_elems; ag.target = target; ag.world = world; ag.rank = rank;
+  const long long unit_elems = chunk_elems * world;
+  ag.n_seg = static_cast<int>((unit_elems + SEG_ELEMS - 1) / SEG_ELEMS);
+  const long long off = static_cast<const __nv_bfloat16*>(b) - static_cast<const __nv_bfloat16*>(local);
+  const bool b_in_unit = off >= 0 && off + static_cast<long long>(N) * K <= unit_elems && ldb == (b_mn ? N : K);
+  ag.b_offset = b_in_unit ? off : -1;
+  ag.first_seg = b_in_unit ? off / SEG_ELEMS : 0;
+  gemm_launch_ag(a, lda, a_mn, b, ldb, b_mn, d, ldd, d2, ldd2, aux, ld_aux, M, N, K, epi, accumulate, num_sms, stream, &ag);
 }
 
 void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long long ldb, bool b_mn, void* d,
@@ -756,21 +751,16 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
   GemmParams p{reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, M, N, K, accumulate, GatherParams{}, pick_group_m(N, num_sms), 1, static_cast<__nv_bfloat16*>(d2), ldd2, nullptr, nullptr};
   if (ag) {
     p.ag = *ag;
-    if (a_mn || b_mn) throw std::runtime_error("all-gather ⊕ GEMM needs K-major operands");
-    // weight rows arrive in address order: sweep all m-blocks of one n-block before the next n-block, so the first wave needs
-    // only the first 256 weight rows (1 MB) and later waves consume rows long after they landed; A stays L2-resident.
-    p.group_m = (M + BM - 1) / BM;
-  }
-  if (ag) {
-    if (epi == EPI_STORE) return launch_one<false, false, EPI_STORE, true>(tA, tB, tD, tD2, p, num_sms, stream);
-    if (epi == EPI_GELU) return launch_one<false, false, EPI_GELU, true>(tA, tB, tD, tD2, p, num_sms, stream);
-    if (epi == EPI_RESIDUAL) return launch_one<false, false, EPI_RESIDUAL, true>(tA, tB, tD, tD2, p, num_sms, stream);
-    throw std::runtime_error("all-gather ⊕ GEMM: unsupported epilogue");
+    // weight rows arrive in address order: with a K-major B that is part of the gathered unit, sweep all m-blocks of one n-block
+    // before the next n-block, so the first wave needs only the first 256 weight rows and later waves consume rows long after
+    // they landed (A stays L2-resident)
+    if (ag->b_offset >= 0 && !b_mn) p.group_m = (M + 2 * BM - 1) / (2 * BM);
+    if (!(use_cg2() && M >= 2 * BM)) throw std::runtime_error("all-gather ⊕ GEMM needs the pair kernel (M >= 256)");
   }
   if (use_cg2() && M >= 2 * BM) {
     // pair kernels: each CTA loads half of the B tile -> K-major B needs a 128-row box (MN-major boxes are 64 wide anyway)
     CUtensorMap tB2 = b_mn ? tB : make_tmap_2d(b, 2, N, K, ldb, BK, BN / 2);
-    p.group_m = pick_group_m(N, num_sms / 2);
+    if (!(ag && ag->b_offset >= 0 && !b_mn)) p.group_m = pick_group_m(N, num_sms / 2);
     p.split_k = pick_split_k(((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN), num_sms / 2, (K + BK - 1) / BK, epi, accumulate);
     // second [M, N] tile of the epilogue through TMA boxes (5 operand stages) or through registers (6 stages): the boxes win
     // when the k-loop is short and the epilogue sets the pace (K = 768), the deeper ring when it is long

@@ -105,7 +105,8 @@ class GPTModel:
         H, C = cfg.n_head, cfg.head_dim
         p = cfg.dropout if training else 0.0
         dmlp = dy if p == 0.0 else be.dropout(dy, p, _site_seed(step_seed, micro, layer, 3))
-        be.linear_wgrad(dmlp, s["a"], g["mlp_proj"])
+        # (ZeRO-3 / layer gathers without remat: this first GEMM of the block's backward carries the unit's all-gather)
+        be.linear_wgrad(dmlp, s["a"], g["mlp_proj"], gather=w.get("__gather__"))
         dpre = be.linear_dgrad(dmlp, w["mlp_proj"], gelu_pre=s["pre"])
         be.linear_wgrad(dpre, s["h2"], g["c_fc"])
         dh2 = be.linear_dgrad(dpre, w["c_fc"])

@@ -65,12 +65,13 @@ class B200Backend:
 
     # ---------------------------------------------------------------- helpers
     def _gemm(self, a, a_mn, b, b_mn, d, epi=EPI_STORE, d2=None, aux=None, accumulate=False, gather=None):
-        if gather is not None:
-            # all-gather ⊕ GEMM: the weight's unit is still being pulled from the peers by the first CTAs of this very kernel
-            assert not a_mn and not b_mn and not accumulate
-            self.ext.gemm_ag(a, b, d, epi, d2, aux, gather.peer_ptrs, gather.local, gather.flags, gather.chunk_elems,
-                             gather.target, gather.rank, gather.n_ctas)
+        if gather is not None and not gather.done:
+            # all-gather ⊕ GEMM: this GEMM carries the NVLink pull of the weight unit (copy warps in its own CTAs, csrc/gemm.cu);
+            # if b is one of the unit's weights the kernel synchronises with the pull segment by segment
+            self.ext.gemm_ag(a, a_mn, b, b_mn, d, epi, d2, aux, accumulate, gather.peer_ptrs, gather.local, gather.flags,
+                             gather.chunk_elems, gather.target, gather.rank)
             gather.done = True
+            gather.carried_by = "wgrad" if epi == EPI_F32 else ("dgrad" if b_mn else "fwd")
         else:
             self.ext.gemm(a, a_mn, b, b_mn, d, epi, d2, aux, accumulate)
         self.launches += 1
@@ -159,19 +160,19 @@ class B200Backend:
             self._gemm(x, False, w, False, y, EPI_STORE, gather=gather)
         return y
 
-    def linear_dgrad(self, dy, w, gelu_pre=None, dres=None):
+    def linear_dgrad(self, dy, w, gelu_pre=None, dres=None, gather=None):
         M, K = dy.shape[0], w.shape[1]
         dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
         if gelu_pre is not None:
-            self._gemm(dy, False, w, True, dx, EPI_DGELU, aux=gelu_pre)
+            self._gemm(dy, False, w, True, dx, EPI_DGELU, aux=gelu_pre, gather=gather)
         elif dres is not None:
-            self._gemm(dy, False, w, True, dx, EPI_RESIDUAL, aux=dres)
+            self._gemm(dy, False, w, True, dx, EPI_RESIDUAL, aux=dres, gather=gather)
         else:
-            self._gemm(dy, False, w, True, dx, EPI_STORE)
+            self._gemm(dy, False, w, True, dx, EPI_STORE, gather=gather)
         return dx
 
-    def linear_wgrad(self, dy, x, dw_acc):
-        self._gemm(dy, True, x, True, dw_acc, EPI_F32, accumulate=True)
+    def linear_wgrad(self, dy, x, dw_acc, gather=None):
+        self._gemm(dy, True, x, True, dw_acc, EPI_F32, accumulate=True, gather=gather)
 
     # ---------------------------------------------------------------- QK-LN + RoPE
     def qkln_rope_fwd(self, qkv, q_gain, k_gain, B, T, H, C, eps=1e-6):

@@ -92,7 +92,7 @@ class TorchBackend:
             y = y + res
         return y
 
-    def linear_dgrad(self, dy, w, gelu_pre=None, dres=None):
+    def linear_dgrad(self, dy, w, gelu_pre=None, dres=None, gather=None):
         """dx = dy @ w, optionally ·gelu'(pre) (K8 backward) and/or + dres."""
         dx = dy @ w
         if gelu_pre is not None:
@@ -101,7 +101,7 @@ class TorchBackend:
             dx = dx + dres
         return dx
 
-    def linear_wgrad(self, dy, x, dw_acc: torch.Tensor) -> None:
+    def linear_wgrad(self, dy, x, dw_acc: torch.Tensor, gather=None) -> None:
         """dw_acc (fp32 or wider) += dyᵀ @ x."""
         if dw_acc.dtype == dy.dtype:
             dw_acc.addmm_(dy.t(), x)

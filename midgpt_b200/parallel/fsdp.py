@@ -100,6 +100,7 @@ class FSDPEngine:
         self._need_gather = True
         self._micro_is_last = True
         self._pending_reduce: tp.List[int] = []
+        self._open_specs: tp.Dict[int, tp.Any] = {}
         self._exposed_pairs: tp.List[tp.Tuple[tp.Any, tp.Any]] = []
         self.last_grad_norm: torch.Tensor | None = None
         if self.comm == "fused" and self.S > 1:
@@ -203,9 +204,11 @@ class FSDPEngine:
             u.pool_slot = slot
             u.lp_full = self._pool[slot][: u.padded]
             u.lp_full[self.sr * u.shard:(self.sr + 1) * u.shard].copy_(u.lp_shard)       # local chunk
-            gemm_first = unit >= 1 and (self._direction >= 0 or self.cfg.engine.remat == "block")
-            if gemm_first:
+            if unit >= 1:
+                # blocks and the LM head: the first GEMM the model launches for this unit carries the pull -- the forward QKV /
+                # LM-head GEMM consumes the rows as they land (X1), in backward the first weight-gradient GEMM simply hides it (X2)
                 spec = self.fused.gather_spec(u)
+                self._open_specs[unit] = spec
             else:
                 self.fused.all_gather(u)
         views = P.unit_views(u.spec, u.lp_full)
@@ -230,6 +233,9 @@ class FSDPEngine:
         u = self.units[unit]
         if u.lp_full is None:
             return
+        spec = self._open_specs.pop(unit, None)
+        if spec is not None and not spec.done:
+            raise RuntimeError(f"FSDP unit {unit} was released but no GEMM carried its all-gather: its weights were never complete")
         if self.cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())

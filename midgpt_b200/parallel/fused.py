@@ -30,15 +30,16 @@ from ..optim import step_scalars, clip_factor_from_sumsq
 
 
 class GatherSpec:
-    """Everything the all-gather ⊕ GEMM kernel needs to pull one unit's remote chunks while it multiplies (csrc/gemm.cu)."""
+    """Everything a GEMM needs to carry the all-gather of one unit while it multiplies (csrc/gemm.cu: copy warps in every CTA)."""
 
-    def __init__(self, peer_ptrs, local, flags, chunk_elems, target, rank, n_ctas):
+    def __init__(self, peer_ptrs, local, flags, chunk_elems, target, rank, n_ctas=0):
         self.peer_ptrs, self.local, self.flags = peer_ptrs, local, flags
-        self.chunk_elems, self.target, self.rank, self.n_ctas = chunk_elems, target, rank, n_ctas
+        self.chunk_elems, self.target, self.rank = chunk_elems, target, rank
         self.done = False
+        self.carried_by = None
 
 
-AG_CTAS = 24     # CTAs of the all-gather ⊕ GEMM grid that act as NVLink copy engines (13 x 16 B loads in flight per thread)
+AG_CTAS = 32     # CTAs of the stand-alone NVLink pull kernel (units whose first consumer is not a GEMM: the embedding)
 SEG_ELEMS = 32768    # flag granularity (must match csrc/gemm.cu)
 
 
@@ -92,7 +93,7 @@ class FusedComm:
             soff += u.shard
         if self.layer_mode:
             n_slots = len(engine._pool)
-            n_seg = max(u.padded for u in engine.units) // SEG_ELEMS + 2
+            n_seg = max(u.padded for u in engine.units) // SEG_ELEMS + 2 + 16
             self.slot_flags = [torch.zeros(n_seg, dtype=torch.int32, device=dev) for _ in range(n_slots)]
             self.slot_calls = [0] * n_slots
             self._scratch_flags = torch.zeros(8, dtype=torch.int32, device=dev)     # stand-alone pulls are ordered by the stream
