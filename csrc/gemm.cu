@@ -126,7 +126,7 @@ struct WorkIter {
   }
 };
 
-template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false, bool CG2 = false, bool AUXB = false>
+template <bool A_MN, bool B_MN, int EPI, bool AG = false, bool FP8 = false, bool CG2 = false, bool AUXB = false, bool CARRY = false>
 __global__ void __launch_bounds__(CG2 ? NUM_THREADS + COPY_THREADS : NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
@@ -138,12 +138,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // 16-byte-per-lane global accesses with one row per lane cost 32 L1 wavefronts per instruction, and those wavefronts compete
   // with the tensor core's operand reads for the same shared-memory / L1 bandwidth.
   constexpr bool HAS_AUX = (EPI == EPI_RESIDUAL || EPI == EPI_DGELU);
-  constexpr bool AUXBUF = CG2 && AUXB && (HAS_AUX || EPI == EPI_GELU);
-  constexpr int NST = CG2 ? (AUXBUF ? 5 : 6) : STAGES;           // pipeline depth
+  constexpr bool AUXBUF = CG2 && AUXB && !CARRY && (HAS_AUX || EPI == EPI_GELU);
+  // CARRY: this instantiation can carry the all-gather of an FSDP unit (see GatherParams): the sixth operand stage becomes the
+  // 2 x 16 KB bulk-copy rings of the two copy warps.
+  static_assert(!CARRY || CG2, "only pair kernels carry a gather");
+  constexpr int NST = CG2 ? ((AUXBUF || CARRY) ? 5 : 6) : STAGES;   // pipeline depth
   constexpr int STG = CG2 ? 2 * A_STAGE_BYTES : STAGE_BYTES;     // bytes per stage in this CTA (A 16 KB + B 16 KB (half) | 32 KB)
-  static_assert(NST * STG + (AUXBUF ? 8 * 4096 : 0) == STAGES * STAGE_BYTES, "operand ring (+ aux boxes) must end where the barriers begin");
+  static_assert(NST * STG + ((AUXBUF || CARRY) ? 8 * 4096 : 0) == STAGES * STAGE_BYTES, "operand ring (+ aux boxes / copy rings) must end where the barriers begin");
   uint8_t* sC = smem + NST * STG;                                // 8 x 4 KB staging boxes
-  uint8_t* sAux = sC + 8 * 4096;                                 // 8 x 4 KB aux boxes (AUXBUF only)
+  uint8_t* sAux = sC + 8 * 4096;                                 // 8 x 4 KB aux boxes (AUXBUF) | 2 x 4 x 4 KB copy rings (CARRY)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES);
   uint64_t* empty_bar = full_bar + NST;
   uint64_t* tfull_bar = empty_bar + NST;
@@ -169,7 +172,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    if (AUXBUF)
+    if (AUXBUF || CARRY)
       for (int w = 0; w < 8; ++w) mbar_init(&aux_bar[w], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
@@ -187,7 +190,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const bool carry = CG2 && p.ag.n_seg > 0;               // this launch carries the gather of an FSDP unit (copy warps 10-11)
+  const bool carry = CARRY && p.ag.n_seg > 0;             // this launch carries the gather of an FSDP unit (copy warps 10-11)
   const bool poll = carry && p.ag.b_offset >= 0;           // ... and its own B operand is part of that unit
   const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_stride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -325,56 +328,54 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 2 + EPI_THREADS / 32) {
     // ===================== copy warps (pair kernels): the all-gather this GEMM carries =====================
-    if (carry) {
-      const int tid = static_cast<int>(threadIdx.x) - NUM_THREADS;          // 0..63
+    // One elected thread per copy warp drives a ring of four 4 KB bulk copies: peer shard --cp.async.bulk--> shared memory
+    // --cp.async.bulk--> local unit buffer.  The bytes never touch registers or the LSU: measured, ordinary global loads issued
+    // next to a running tcgen05 GEMM see ~17 us of latency (its TMA operand traffic owns the SM's path to L2), which capped every
+    // register-based copy loop -- pull or multicast push, 24 dedicated CTAs or 148 x 64 threads -- at ~140 GB/s; the TMA path is
+    // the one the GEMM's own operands use and is served in about a microsecond.
+    if (CARRY && carry && lane == 0) {
+      const int w = warp - (2 + EPI_THREADS / 32);                          // 0 | 1
+      uint8_t* ring = sAux + w * (4 * 4096);
+      uint64_t* full = aux_bar + w * 4;
       const long long unit_elems = p.ag.chunk_elems * p.ag.world;
       const long long loc0 = static_cast<long long>(p.ag.rank) * p.ag.chunk_elems, loc1 = loc0 + p.ag.chunk_elems;
-      constexpr int PER_RD = 16;                                            // 16 x 16 B in flight per thread
-      constexpr int ROUNDS = static_cast<int>(SEG_ELEMS / 8) / (COPY_THREADS * PER_RD);   // 4
-      for (long long i = blockIdx.x; i < p.ag.n_seg; i += gridDim.x) {
+      uint32_t head = 0, tail = 0;                                          // pieces loaded / pieces stored
+      long long q_dst[4];
+      uint32_t q_bytes[4];
+      auto drain_one = [&]() {                                              // oldest piece: landed in shared memory -> store it
+        const uint32_t sl = tail & 3;
+        mbar_wait(&full[sl], (tail >> 2) & 1);
+        bulk_store_1d(p.ag.local + q_dst[sl], ring + sl * 4096, q_bytes[sl]);
+        tma_commit_group();
+        ++tail;
+      };
+      for (long long i = static_cast<long long>(blockIdx.x) * 2 + w; i < p.ag.n_seg; i += 2LL * gridDim.x) {
         long long seg = p.ag.first_seg + i;
         if (seg >= p.ag.n_seg) seg -= p.ag.n_seg;
         const long long e0 = seg * SEG_ELEMS, e1 = (e0 + SEG_ELEMS < unit_elems) ? e0 + SEG_ELEMS : unit_elems;
         if (e0 >= loc0 && e1 <= loc1) continue;                              // owned by this rank: already in place
-        // one 64-bit division per segment: a 64 KB segment touches at most two chunks (unless the unit is tiny)
-        const int c0 = static_cast<int>(e0 / p.ag.chunk_elems);
-        const long long c0_end = static_cast<long long>(c0 + 1) * p.ag.chunk_elems;
-        const int c1 = c0 + 1 < p.ag.world ? c0 + 1 : c0;
-        const __nv_bfloat16* base0 = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c0]) - static_cast<long long>(c0) * p.ag.chunk_elems;
-        const __nv_bfloat16* base1 = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c1]) - static_cast<long long>(c1) * p.ag.chunk_elems;
-#pragma unroll 1
-        for (int rd = 0; rd < ROUNDS; ++rd) {
-          uint4 v[PER_RD];
-          uint32_t live = 0;
-#pragma unroll
-          for (int u = 0; u < PER_RD; ++u) {
-            const long long e = e0 + (static_cast<long long>(rd * PER_RD + u) * COPY_THREADS + tid) * 8;
-            if (e < e1) {
-              const bool second = e >= c0_end;
-              int c = second ? c1 : c0;
-              const __nv_bfloat16* base = second ? base1 : base0;
-              if (p.ag.chunk_elems < SEG_ELEMS) {      // tiny unit: a segment may span more than two chunks -- exact, slow path
-                c = static_cast<int>(e / p.ag.chunk_elems);
-                base = reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[c]) - static_cast<long long>(c) * p.ag.chunk_elems;
-              }
-              if (c != p.ag.rank) {
-                const uint4* src = reinterpret_cast<const uint4*>(base + e);
-                asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src));
-                live |= 1u << u;
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < PER_RD; ++u)
-            if (live & (1u << u))
-              *reinterpret_cast<uint4*>(p.ag.local + e0 + (static_cast<long long>(rd * PER_RD + u) * COPY_THREADS + tid) * 8) = v[u];
+        for (long long cur = e0; cur < e1;) {
+          const long long owner = cur / p.ag.chunk_elems;
+          const long long own_end = (owner + 1) * p.ag.chunk_elems;
+          const long long lim = e1 < own_end ? e1 : own_end;
+          if (owner == p.ag.rank) { cur = lim; continue; }
+          const long long left = (lim - cur) * 2;
+          const uint32_t bytes = left < 4096 ? static_cast<uint32_t>(left) : 4096u;
+          if (head - tail == 4) drain_one();
+          if (head >= 4) tma_wait_group_read<0>();                           // the slot's previous store has read its bytes
+          const uint32_t sl = head & 3;
+          mbar_expect_tx(&full[sl], bytes);
+          bulk_load_1d(ring + sl * 4096, reinterpret_cast<const __nv_bfloat16*>(p.ag.peer[owner]) + (cur - owner * p.ag.chunk_elems), bytes, &full[sl]);
+          q_dst[sl] = cur;
+          q_bytes[sl] = bytes;
+          ++head;
+          cur += bytes / 2;
         }
+        while (tail < head) drain_one();
+        tma_wait_group<0>();                                                 // the segment's bytes are in the local buffer
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         __threadfence();
-        named_bar_sync(3, COPY_THREADS);
-        if (tid == 0) {
-          asm volatile("fence.proxy.async.global;" ::: "memory");           // consumed by TMA (async proxy)
-          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + seg), "r"(p.ag.target) : "memory");
-        }
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ag.flags + seg), "r"(p.ag.target) : "memory");
       }
     }
   } else {
@@ -657,10 +658,10 @@ static bool use_auxbuf(int K) {
   return mode < 0 ? K <= 1024 : mode != 0;
 }
 
-template <bool A_MN, bool B_MN, int EPI, bool FP8 = false, bool AUXB = false>
+template <bool A_MN, bool B_MN, int EPI, bool FP8 = false, bool AUXB = false, bool CARRY = false>
 static void launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tD2,
                         const GemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, false, FP8, true, AUXB>;
+  auto kern = gemm_bf16_tcgen05<A_MN, B_MN, EPI, false, FP8, true, AUXB, CARRY>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -722,7 +723,8 @@ void gemm_launch_ag_raw(const void* a, long long lda, bool a_mn, const void* b, 
                         long long ldd2, const void* aux, long long ld_aux, int M, int N, int K, int epi, int accumulate, int num_sms,
                         cudaStream_t stream, const long long* peer_ptrs, void* local, unsigned int* flags, long long chunk_elems,
                         unsigned int target, int world, int rank) {
-  if (!(use_cg2() && M >= 2 * BM)) {
+  const bool has_variant = (!a_mn && !b_mn && (epi == EPI_STORE || epi == EPI_GELU)) || (a_mn && b_mn && epi == EPI_F32) || (!a_mn && b_mn && epi == EPI_DGELU);
+  if (!(use_cg2() && M >= 2 * BM && has_variant)) {
     ag_pull(peer_ptrs, local, chunk_elems, rank, world, flags + (chunk_elems * world + SEG_ELEMS - 1) / SEG_ELEMS, 32, stream);
     return gemm_launch_ag(a, lda, a_mn, b, ldb, b_mn, d, ldd, d2, ldd2, aux, ld_aux, M, N, K, epi, accumulate, num_sms, stream, nullptr);
   }
@@ -764,6 +766,13 @@ void gemm_launch_ag(const void* a, long long lda, bool a_mn, const void* b, long
     p.split_k = pick_split_k(((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN), num_sms / 2, (K + BK - 1) / BK, epi, accumulate);
     // second [M, N] tile of the epilogue through TMA boxes (5 operand stages) or through registers (6 stages): the boxes win
     // when the k-loop is short and the epilogue sets the pace (K = 768), the deeper ring when it is long
+    if (ag) {      // instantiations that can carry a gather: forward store (QKV / LM head), MLP-in (gelu), wgrad, the first dgrad of a block
+      if (!a_mn && !b_mn && epi == EPI_STORE) return launch_pair<false, false, EPI_STORE, false, false, true>(tA, tB2, tD, tD2, p, num_sms, stream);
+      if (!a_mn && !b_mn && epi == EPI_GELU) return launch_pair<false, false, EPI_GELU, false, false, true>(tA, tB2, tD, tD2, p, num_sms, stream);
+      if (a_mn && b_mn && epi == EPI_F32) return launch_pair<true, true, EPI_F32, false, false, true>(tA, tB2, tD, tD2, p, num_sms, stream);
+      if (!a_mn && b_mn && epi == EPI_DGELU) return launch_pair<false, true, EPI_DGELU, false, false, true>(tA, tB2, tD, tD2, p, num_sms, stream);
+      throw std::runtime_error("all-gather ⊕ GEMM: this (layout, epilogue) has no carrying instantiation");
+    }
     const bool auxb = use_auxbuf(K);
 #define MG_PAIR(AM, BM_, E) \
     if (a_mn == AM && b_mn == BM_ && epi == E) return launch_pair<AM, BM_, E>(tA, tB2, tD, tD2, p, num_sms, stream);

@@ -57,6 +57,16 @@ class DictProvider:
     def grads_ready(self, unit): self.ready_order.append(unit)
 
 
+def _carry(w: W):
+    """The all-gather a GEMM of this unit should carry next (ZeRO-3 layer mode, all-gather ⊕ GEMM): the unit's own gather if no
+    kernel has taken it yet, else the prefetch of the next unit of the schedule; None when there is nothing (left) to carry."""
+    for key in ("__gather__", "__prefetch__"):
+        spec = w.get(key)
+        if spec is not None and not spec.done:
+            return spec
+    return None
+
+
 def _site_seed(step_seed: int, micro: int, layer: int, site: int) -> int:
     return (step_seed * 1000003 + micro * 7919 + layer * 31 + site) & 0x7FFFFFFFFFFFFFFF
 
@@ -89,7 +99,7 @@ class GPTModel:
                     x2 = x + be.dropout(be.linear_fwd(o, w["attn_proj"]), p, _site_seed(step_seed, micro, layer, 2))
             h2, rstd2 = be.rmsnorm_fwd(x2, 1e-6)
             with self._range("mlp"):
-                pre, a = be.linear_fwd(h2, w["c_fc"], act="gelu")
+                pre, a = be.linear_fwd(h2, w["c_fc"], act="gelu", gather=_carry(w))     # MLP-in GEMM: carries the NEXT unit's gather
                 if p == 0.0:
                     y = be.linear_fwd(a, w["mlp_proj"], res=x2)
                 else:
@@ -106,9 +116,9 @@ class GPTModel:
         p = cfg.dropout if training else 0.0
         dmlp = dy if p == 0.0 else be.dropout(dy, p, _site_seed(step_seed, micro, layer, 3))
         # (ZeRO-3 / layer gathers without remat: this first GEMM of the block's backward carries the unit's all-gather)
-        be.linear_wgrad(dmlp, s["a"], g["mlp_proj"], gather=w.get("__gather__"))
+        be.linear_wgrad(dmlp, s["a"], g["mlp_proj"], gather=_carry(w))
         dpre = be.linear_dgrad(dmlp, w["mlp_proj"], gelu_pre=s["pre"])
-        be.linear_wgrad(dpre, s["h2"], g["c_fc"])
+        be.linear_wgrad(dpre, s["h2"], g["c_fc"], gather=_carry(w))
         dh2 = be.linear_dgrad(dpre, w["c_fc"])
         dx2 = be.rmsnorm_bwd(dh2, s["x2"], s["rstd2"], dres=dy)
         dproj = dx2 if p == 0.0 else be.dropout(dx2, p, _site_seed(step_seed, micro, layer, 2))
@@ -152,7 +162,8 @@ class GPTModel:
             # final norm + fused LM head / CE (forward and backward in one pass)
             wh = wp.acquire(L + 1)
             hf, rstdf = be.rmsnorm_fwd(x, 1e-5)
-            loss_sum, dhf = be.lmhead_ce(hf, wh["lm_head"], targets, wp.grads(L + 1)["lm_head"], grad_scale, gather=wh.get("__gather__"))
+            loss_sum, dhf = be.lmhead_ce(hf, wh["lm_head"], targets, wp.grads(L + 1)["lm_head"], grad_scale, gather=wh.get("__gather__"),
+                                         prefetch=wh.get("__prefetch__"))
             wp.release(L + 1)
             wp.grads_ready(L + 1)
             dx = be.rmsnorm_bwd(dhf, x, rstdf)

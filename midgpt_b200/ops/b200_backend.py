@@ -62,6 +62,7 @@ class B200Backend:
         self._rope: tp.Dict[tp.Tuple[int, int], tp.Tuple[torch.Tensor, torch.Tensor]] = {}
         self._logits_ws: torch.Tensor | None = None
         self.launches = 0          # kernels launched through this backend (bench.py reports it)
+        self.carried = 0           # GEMM launches that carried an FSDP unit's all-gather (all-gather ⊕ GEMM)
 
     # ---------------------------------------------------------------- helpers
     def _gemm(self, a, a_mn, b, b_mn, d, epi=EPI_STORE, d2=None, aux=None, accumulate=False, gather=None):
@@ -71,6 +72,7 @@ class B200Backend:
             self.ext.gemm_ag(a, a_mn, b, b_mn, d, epi, d2, aux, accumulate, gather.peer_ptrs, gather.local, gather.flags,
                              gather.chunk_elems, gather.target, gather.rank)
             gather.done = True
+            self.carried += 1
             gather.carried_by = "wgrad" if epi == EPI_F32 else ("dgrad" if b_mn else "fwd")
         else:
             self.ext.gemm(a, a_mn, b, b_mn, d, epi, d2, aux, accumulate)
@@ -220,7 +222,7 @@ class B200Backend:
         self._gemm(h, False, w, False, buf[:, :V], EPI_STORE, gather=gather)
         return buf[:, :V]
 
-    def lmhead_ce(self, h, w, targets, dw_acc=None, grad_scale: float = 0.0, chunk: int = 8192, gather=None):
+    def lmhead_ce(self, h, w, targets, dw_acc=None, grad_scale: float = 0.0, chunk: int = 8192, gather=None, prefetch=None):
         M, V = h.shape[0], w.shape[0]
         vpad = (V + 7) // 8 * 8
         tg = targets.reshape(-1).to(torch.int32).contiguous()
@@ -231,7 +233,8 @@ class B200Backend:
             buf = self._logits_buf(e - s, vpad)
             logits = buf[:, :V]
             hc = h[s:e]
-            self._gemm(hc, False, w, False, logits, EPI_STORE, gather=gather if s == 0 else None)
+            carry = gather if (gather is not None and not gather.done) else prefetch     # own gather first, then the next unit's
+            self._gemm(hc, False, w, False, logits, EPI_STORE, gather=carry)
             self.ext.ce_chunk(buf, tg[s:e], loss_sum, V, float(grad_scale), dw_acc is not None)
             self.launches += 1
             if dw_acc is not None:

@@ -223,7 +223,7 @@ class TorchBackend:
     def lmhead_logits(self, h, w, gather=None):
         return h @ w.t()
 
-    def lmhead_ce(self, h, w, targets, dw_acc=None, grad_scale: float = 0.0, chunk: int = 8192, gather=None):
+    def lmhead_ce(self, h, w, targets, dw_acc=None, grad_scale: float = 0.0, chunk: int = 8192, gather=None, prefetch=None):
         """Σ_tokens CE(h·wᵀ, targets) in fp32 without materialising [M,V] at once.
 
         If ``dw_acc`` is given the backward is fused: returns (loss_sum, dh) and accumulates

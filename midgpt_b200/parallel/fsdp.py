@@ -75,8 +75,7 @@ class FSDPEngine:
         self._comm_auto = self.comm == "auto"
         if self.comm == "auto":
             # product path when it applies (NVLink domain + hand-written backend), library collectives otherwise
-            fused_ok = (mesh.backend == "nccl" and self.S > 1 and getattr(backend, "name", "") == "b200"
-                        and self.gather_mode == "step")
+            fused_ok = mesh.backend == "nccl" and self.S > 1 and getattr(backend, "name", "") == "b200"
             self.comm = "fused" if fused_ok else (mesh.backend if mesh.backend != "none" else "none")
         self.comm_stream = torch.cuda.Stream(self.device) if self.cuda else None
         self.fused = None                                # parallel.fused.FusedComm when comm == "fused"
@@ -192,28 +191,47 @@ class FSDPEngine:
             torch.cuda.current_stream().wait_event(u.gathered_event)
         return P.unit_views(u.spec, u.lp_full)
 
-    def _acquire_fused_layer(self, unit: int) -> tp.Dict[str, torch.Tensor]:
-        """ZeRO-3 gathers with no collective call: the unit's first K-major GEMM pulls the remote chunks itself
-        (all-gather ⊕ GEMM); units whose first consumer is not such a GEMM use the stand-alone NVLink pull kernel."""
+    def _open_gather(self, unit: int):
+        """Give ``unit`` a pool slot, put the locally owned chunk in place and return the descriptor of its gather (to be carried
+        by a GEMM).  None if the unit is already resident / open, or no slot is free."""
         u = self.units[unit]
-        spec = None
+        if u.lp_full is not None or not self._pool_free:
+            return None
+        slot = self._pool_free.pop(0)
+        u.pool_slot = slot
+        u.lp_full = self._pool[slot][: u.padded]
+        u.lp_full[self.sr * u.shard:(self.sr + 1) * u.shard].copy_(u.lp_shard)       # local chunk
+        if unit == 0:
+            self.fused.all_gather(u)           # the embedding's first consumer is a gather kernel, not a GEMM: stand-alone NVLink pull
+            return None
+        spec = self.fused.gather_spec(u)
+        self._open_specs[unit] = spec
+        return spec
+
+    def _acquire_fused_layer(self, unit: int) -> tp.Dict[str, torch.Tensor]:
+        """ZeRO-3 gathers with no collective call (all-gather ⊕ GEMM, csrc/gemm.cu): every unit's gather is CARRIED by a GEMM.
+        ``__prefetch__``: the gather of the NEXT unit of the schedule, carried by this unit's MLP-in GEMM (forward) / first
+        weight-gradient GEMM (backward) -- a whole GEMM ahead of its first consumer, so nothing waits for NVLink.
+        ``__gather__``: this unit's own gather when nobody carried it yet (first unit of a pass, eval paths): its first GEMM
+        carries it and -- if that GEMM multiplies one of the unit's weights -- consumes the rows as they land."""
+        u = self.units[unit]
         if u.lp_full is None:
             if not self._pool_free:
                 raise RuntimeError("FSDP pool exhausted: a unit was acquired twice without release")
-            slot = self._pool_free.pop(0)
-            u.pool_slot = slot
-            u.lp_full = self._pool[slot][: u.padded]
-            u.lp_full[self.sr * u.shard:(self.sr + 1) * u.shard].copy_(u.lp_shard)       # local chunk
-            if unit >= 1:
-                # blocks and the LM head: the first GEMM the model launches for this unit carries the pull -- the forward QKV /
-                # LM-head GEMM consumes the rows as they land (X1), in backward the first weight-gradient GEMM simply hides it (X2)
-                spec = self.fused.gather_spec(u)
-                self._open_specs[unit] = spec
-            else:
-                self.fused.all_gather(u)
+            self._open_gather(unit)
         views = P.unit_views(u.spec, u.lp_full)
-        if spec is not None:
-            views["__gather__"] = spec
+        own = self._open_specs.get(unit)
+        if own is not None and not own.done:
+            views["__gather__"] = own
+        nxt = unit + (1 if self._direction >= 0 else -1)
+        if unit == len(self.units) - 1:            # after the LM head the schedule turns around -- if there is a backward pass at all
+            nxt = unit - 1 if self._will_backward else -1
+        if 1 <= nxt < len(self.units):
+            pre = self._open_specs.get(nxt)
+            if pre is None:
+                pre = self._open_gather(nxt)
+            if pre is not None and not pre.done:
+                views["__prefetch__"] = pre
         return views
 
     def _prefetch_candidates(self, unit: int) -> tp.List[int]:
@@ -236,6 +254,10 @@ class FSDPEngine:
         spec = self._open_specs.pop(unit, None)
         if spec is not None and not spec.done:
             raise RuntimeError(f"FSDP unit {unit} was released but no GEMM carried its all-gather: its weights were never complete")
+        if unit == len(self.units) - 1:            # the schedule turns around at the LM head
+            self._direction = -1
+        elif unit == 0:
+            self._direction = 1
         if self.cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
@@ -246,11 +268,6 @@ class FSDPEngine:
             # the pool slot (same data_ptr, same shapes) will hold another unit's weights next: cached e4m3 copies keyed on
             # the pointer would silently be another layer's weights
             self.be.notify_weights_updated()
-        # after the last forward unit the schedule turns around
-        if unit == len(self.units) - 1:
-            self._direction = -1
-        elif unit == 0:
-            self._direction = 1
 
     def grads(self, unit: int) -> tp.Dict[str, torch.Tensor]:
         u = self.units[unit]
@@ -288,8 +305,13 @@ class FSDPEngine:
             D.all_reduce_avg(u.grad_shard, m.replica_group, m.backend)
 
     # ------------------------------------------------------------------ one optimizer step
-    def begin_step(self) -> None:
+    _will_backward = True
+
+    def begin_step(self, backward: bool = True) -> None:
+        """``backward=False`` (evaluation / sampling): the forward pass is not followed by a backward sweep, so the LM head does
+        not prefetch the last block again."""
         self._direction = 1
+        self._will_backward = backward
         self.gather_all()
 
     def set_micro(self, is_last: bool) -> None:
@@ -331,6 +353,7 @@ class FSDPEngine:
         st = {"nccl_collectives": D.COLLECTIVE_CALLS["n"]}
         if self.fused is not None:
             st.update(self.fused.stats)
+            st["gemm_ag"] = getattr(self.be, "carried", 0)        # GEMM launches that carried an all-gather
         return st
 
     def optimizer_step(self) -> torch.Tensor:

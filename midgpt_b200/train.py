@@ -86,7 +86,7 @@ class Trainer:
     @torch.no_grad()
     def eval_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         eng, m = self.engine, self.mesh
-        eng.begin_step()
+        eng.begin_step(backward=False)
         tot = torch.zeros((), dtype=torch.float32, device=m.device)
         n = x.shape[0]
         mb = min(self.micro_bs, n)
