@@ -76,7 +76,7 @@ def main():
     for name, mc in (("rs_sumsq_p2p", 0), ("rs_sumsq_multimem", mc_g)):
         if name.endswith("multimem") and not mc:
             continue
-        t = timeit(lambda: ext.rs_sumsq(gp, mc, out, ss, rank * shard, rank), pre=barrier)
+        t = timeit(lambda: ext.rs_sumsq(gp, mc, out, ss, rank * shard, rank, False, True), pre=barrier)
         res.append({"kernel": name, "ms": t, "nvlink_GBs_per_gpu": by / t / 1e6, "frac_of_770GBs": by / (t * 1e-3) / NVLINK, "frac_of_900GBs": by / (t * 1e-3) / LINK_RATE})
     t = timeit(lambda: dist.reduce_scatter_tensor(out, grad, op=dist.ReduceOp.AVG))
     res.append({"kernel": "nccl_reduce_scatter_fp32", "ms": t, "nvlink_GBs_per_gpu": by / t / 1e6, "frac_of_770GBs": by / (t * 1e-3) / NVLINK, "frac_of_900GBs": by / (t * 1e-3) / LINK_RATE})

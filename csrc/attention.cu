@@ -1337,8 +1337,10 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
 #undef MG_BWD2
   }
   check("attn_bwd");
-  dq_convert_kernel<<<num_sms * 8, 256, 0, s>>>(dq_accum, static_cast<__nv_bfloat16*>(dq), static_cast<long long>(B) * T, H * C, dqkv_row_stride);
-  check("dq_convert");
+  if (dq != nullptr) {      // dq == nullptr: the caller consumes the fp32 accumulator directly (qkln_rope_bwd reads and clears it)
+    dq_convert_kernel<<<num_sms * 8, 256, 0, s>>>(dq_accum, static_cast<__nv_bfloat16*>(dq), static_cast<long long>(B) * T, H * C, dqkv_row_stride);
+    check("dq_convert");
+  }
 }
 
 }  // namespace mg

@@ -25,7 +25,7 @@ void rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* d
 void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const float* sin_t, const float* cos_t, void* qk,
                    float* stats, long long M, int T, int H, int C, float eps, cudaStream_t s);
 void qkln_rope_bwd(void* dqkv, const void* qkv_raw, const float* stats, const float* qg, const float* kg, const float* sin_t,
-                   const float* cos_t, float* dqg, float* dkg, long long M, int T, int H, int C, int num_sms, cudaStream_t s);
+                   const float* cos_t, float* dqg, float* dkg, long long M, int T, int H, int C, int num_sms, cudaStream_t s, float* dq_acc);
 void embed_fwd(const void* wte, const int* idx, void* out, long long M, int D, int num_sms, cudaStream_t s);
 void embed_bwd(const void* dx, const int* idx, float* dwte, long long M, int D, int num_sms, cudaStream_t s);
 void ce_chunk(void* logits, long long ldl, const int* targets, float* loss_sum, int rows, int V, float grad_scale,
@@ -42,7 +42,7 @@ void attn_bwd(const void* q, const void* k, const void* v, const void* o, const 
               int num_sms, cudaStream_t s);
 void xrank_barrier(const long long* pad_ptrs, int rank, int world, int slot, unsigned epoch, cudaStream_t s);
 void rs_sumsq(const long long* grad_ptrs, long long mc_ptr, float* out_shard, float* sumsq, long long shard_off, long long n, int rank,
-              int world, int num_sms, cudaStream_t s);
+              int world, int accumulate, int want_sumsq, int num_sms, cudaStream_t s);
 void adamw_allgather(float* p, float* m, float* v, const float* g, const long long* lp_ptrs, long long mc_ptr, long long shard_off,
                      long long n, const float* clip_ptr, float lr, float b1, float b2, float eps, float wd_over_lr_peak, float bc1,
                      float bc2, int world, int num_sms, cudaStream_t s);
@@ -216,13 +216,20 @@ std::vector<at::Tensor> qkln_rope_fwd(const at::Tensor& qkv, const at::Tensor& q
   return {qk, stats};
 }
 void qkln_rope_bwd(at::Tensor& dqkv, const at::Tensor& qkv_raw, const at::Tensor& stats, const at::Tensor& qg, const at::Tensor& kg,
-                   const at::Tensor& sin_t, const at::Tensor& cos_t, at::Tensor& dqg, at::Tensor& dkg, int64_t T, int64_t H, int64_t C) {
+                   const at::Tensor& sin_t, const at::Tensor& cos_t, at::Tensor& dqg, at::Tensor& dkg, int64_t T, int64_t H, int64_t C,
+                   const c10::optional<at::Tensor>& dq_acc) {
   c10::cuda::CUDAGuard guard(dqkv.device());
+  float* accp = nullptr;
+  if (dq_acc.has_value()) {
+    CHECK_F32(*dq_acc);
+    TORCH_CHECK(dq_acc->is_contiguous() && dq_acc->numel() == dqkv.size(0) * H * C, "qkln_rope_bwd: dq_acc must be [M, H*C] fp32");
+    accp = dq_acc->data_ptr<float>();
+  }
   CHECK_BF16(dqkv); CHECK_BF16(qkv_raw); CHECK_F32(stats); CHECK_F32(qg); CHECK_F32(kg); CHECK_F32(dqg); CHECK_F32(dkg);
   TORCH_CHECK(dqkv.is_contiguous() && qkv_raw.is_contiguous() && dqkv.sizes() == qkv_raw.sizes());
   mg::qkln_rope_bwd(dqkv.data_ptr(), qkv_raw.data_ptr(), stats.data_ptr<float>(), qg.data_ptr<float>(), kg.data_ptr<float>(),
                     sin_t.data_ptr<float>(), cos_t.data_ptr<float>(), dqg.data_ptr<float>(), dkg.data_ptr<float>(), dqkv.size(0), T, H, C,
-                    num_sms_of(dqkv), stream());
+                    num_sms_of(dqkv), stream(), accp);
 }
 
 at::Tensor embed_fwd(const at::Tensor& wte, const at::Tensor& idx) {
@@ -292,18 +299,28 @@ std::vector<at::Tensor> attn_fwd(const at::Tensor& q, const at::Tensor& k, const
 }
 
 // dqkv: [B*T, 3*H*C] bf16 output (dq | dk | dv thirds).
+// dq_acc (optional): a ZEROED fp32 [B*T, H*C] accumulator owned by the caller.  With it the kernel leaves dq there (the dq third of
+// the returned tensor is not written) and launches neither the zero-fill nor the fp32->bf16 conversion: qkln_rope_bwd consumes and
+// re-zeroes the accumulator.
 at::Tensor attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& o, const at::Tensor& dout,
-                    const at::Tensor& lse, double dropout_p, int64_t seed) {
+                    const at::Tensor& lse, double dropout_p, int64_t seed, const c10::optional<at::Tensor>& dq_acc) {
   c10::cuda::CUDAGuard guard(q.device());
   CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(o); CHECK_BF16(dout); CHECK_F32(lse);
   const int64_t B = q.size(0), T = q.size(1), H = q.size(2), C = q.size(3);
   TORCH_CHECK(o.is_contiguous() && dout.is_contiguous());
   auto dqkv = at::empty({B * T, 3 * H * C}, q.options());
   auto delta = at::empty({3, B, H, T}, lse.options());   // delta | delta*scale | lse*log2(e)
-  auto dq_accum = at::zeros({B * T, H * C}, lse.options());
+  at::Tensor dq_accum;
+  if (dq_acc.has_value()) {
+    CHECK_F32(*dq_acc);
+    TORCH_CHECK(dq_acc->is_contiguous() && dq_acc->numel() == B * T * H * C, "attn_bwd: dq_acc must be [B*T, H*C] fp32");
+    dq_accum = *dq_acc;
+  } else {
+    dq_accum = at::zeros({B * T, H * C}, lse.options());
+  }
   char* base = static_cast<char*>(dqkv.data_ptr());
   mg::attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(),
-               base, base + H * C * 2, base + 2 * H * C * 2, dq_accum.data_ptr<float>(), B, T, H, C, q.stride(1), k.stride(1), v.stride(1),
+               dq_acc.has_value() ? nullptr : base, base + H * C * 2, base + 2 * H * C * 2, dq_accum.data_ptr<float>(), B, T, H, C, q.stride(1), k.stride(1), v.stride(1),
                3 * H * C, static_cast<float>(dropout_p), static_cast<unsigned long long>(seed), num_sms_of(q), stream());
   return dqkv;
 }
@@ -313,12 +330,13 @@ void xrank_barrier(std::vector<int64_t> pads, int64_t rank, int64_t slot, int64_
   std::vector<long long> p(pads.begin(), pads.end());
   mg::xrank_barrier(p.data(), rank, static_cast<int>(p.size()), slot, static_cast<unsigned>(epoch), stream());
 }
-void rs_sumsq(std::vector<int64_t> grad_ptrs, int64_t mc_ptr, at::Tensor& out_shard, at::Tensor& sumsq, int64_t shard_off, int64_t rank) {
+void rs_sumsq(std::vector<int64_t> grad_ptrs, int64_t mc_ptr, at::Tensor& out_shard, at::Tensor& sumsq, int64_t shard_off, int64_t rank,
+              bool accumulate, bool want_sumsq) {
   c10::cuda::CUDAGuard guard(out_shard.device());
   CHECK_F32(out_shard); CHECK_F32(sumsq);
   std::vector<long long> p(grad_ptrs.begin(), grad_ptrs.end());
   mg::rs_sumsq(p.data(), mc_ptr, out_shard.data_ptr<float>(), sumsq.data_ptr<float>(), shard_off, out_shard.numel(), rank,
-               static_cast<int>(p.size()), num_sms_of(out_shard), stream());
+               static_cast<int>(p.size()), accumulate ? 1 : 0, want_sumsq ? 1 : 0, num_sms_of(out_shard), stream());
 }
 void adamw_allgather(at::Tensor& p, at::Tensor& m, at::Tensor& v, const at::Tensor& g, std::vector<int64_t> lp_ptrs, int64_t mc_ptr,
                      int64_t shard_off, const at::Tensor& clip, double lr, double b1, double b2, double eps, double wd_over_lr_peak,

@@ -71,7 +71,10 @@ __global__ void xrank_barrier_kernel(PeerPtrs pads, int rank, int world, int slo
 template <bool MULTIMEM>
 __global__ void __launch_bounds__(512) rs_sumsq_kernel(PeerPtrs grads, const float* __restrict__ mc_grads, float* __restrict__ out_shard,
                                                        float* __restrict__ sumsq, long long shard_off4, long long n4, int rank, int world,
-                                                       float inv_world) {
+                                                       float inv_world, int accumulate, int want_sumsq) {
+  // accumulate: out_shard += mean (sharded gradient accumulation over micro-steps: the reduce-scatter runs every micro-step and
+  // only a shard-sized fp32 accumulator persists, like the reference's per-microstep sharding constraint, src/train.py:87);
+  // want_sumsq: add Σ out² of the FINAL value to *sumsq (last micro-step only).
   __shared__ float part[16];
   float acc = 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
@@ -89,9 +92,14 @@ __global__ void __launch_bounds__(512) rs_sumsq_kernel(PeerPtrs grads, const flo
       }
     }
     s.x *= inv_world; s.y *= inv_world; s.z *= inv_world; s.w *= inv_world;
+    if (accumulate) {
+      const float4 o = reinterpret_cast<const float4*>(out_shard)[i];
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
     reinterpret_cast<float4*>(out_shard)[i] = s;
     acc += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
   }
+  if (!want_sumsq) return;
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -195,14 +203,14 @@ void xrank_barrier(const long long* pad_ptrs, int rank, int world, int slot, uns
 }
 
 void rs_sumsq(const long long* grad_ptrs, long long mc_ptr, float* out_shard, float* sumsq, long long shard_off, long long n, int rank,
-              int world, int num_sms, cudaStream_t s) {
+              int world, int accumulate, int want_sumsq, int num_sms, cudaStream_t s) {
   if (n % 4 || shard_off % 4) throw std::runtime_error("rs_sumsq: offsets must be multiples of 4 elements");
   PeerPtrs pp = to_peers(grad_ptrs, world);
   const int grid = num_sms * 2;
   if (mc_ptr)
-    rs_sumsq_kernel<true><<<grid, 512, 0, s>>>(pp, reinterpret_cast<const float*>(mc_ptr), out_shard, sumsq, shard_off / 4, n / 4, rank, world, 1.f / world);
+    rs_sumsq_kernel<true><<<grid, 512, 0, s>>>(pp, reinterpret_cast<const float*>(mc_ptr), out_shard, sumsq, shard_off / 4, n / 4, rank, world, 1.f / world, accumulate, want_sumsq);
   else
-    rs_sumsq_kernel<false><<<grid, 512, 0, s>>>(pp, nullptr, out_shard, sumsq, shard_off / 4, n / 4, rank, world, 1.f / world);
+    rs_sumsq_kernel<false><<<grid, 512, 0, s>>>(pp, nullptr, out_shard, sumsq, shard_off / 4, n / 4, rank, world, 1.f / world, accumulate, want_sumsq);
   check_launch_c("rs_sumsq");
 }
 

@@ -237,7 +237,11 @@ __global__ void __launch_bounds__(256, 2) qkln_rope_bwd_kernel(__nv_bfloat16* __
                                                                const float* __restrict__ stats, const float* __restrict__ q_gain,
                                                                const float* __restrict__ k_gain, const float* __restrict__ sin_t,
                                                                const float* __restrict__ cos_t, float* __restrict__ dq_gain,
-                                                               float* __restrict__ dk_gain, unsigned nvec, int T, int H) {
+                                                               float* __restrict__ dk_gain, unsigned nvec, int T, int H,
+                                                               float* __restrict__ dq_acc) {
+  // dq_acc != nullptr: the q gradients are read straight from the attention backward's fp32 accumulator [M, H*C] (and the
+  // accumulator is cleared behind the read, ready for the next layer) instead of from the bf16 dq third of dqkv -- removes the
+  // fp32->bf16 conversion pass and the zero-fill pass between the two kernels.
   constexpr int LPV = C / 8, VPW = 32 / LPV;
   __shared__ float red[2][C];
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) (&red[0][0])[i] = 0.f;
@@ -264,7 +268,14 @@ __global__ void __launch_bounds__(256, 2) qkln_rope_bwd_kernel(__nv_bfloat16* __
       vm[u] = v / twoH;
       vr[u] = v - vm[u] * twoH;
       const size_t off = (static_cast<size_t>(vm[u]) * 3 * H + vr[u]) * C + c0;
-      graw[u] = *reinterpret_cast<const uint4*>(dqkv + off);
+      if (dq_acc != nullptr && vr[u] < static_cast<unsigned>(H)) {
+        float4* ap = reinterpret_cast<float4*>(dq_acc + (static_cast<size_t>(vm[u]) * H + vr[u]) * C + c0);
+        const float4 a0 = ap[0], a1 = ap[1];
+        graw[u] = make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y), pack_bf16(a1.z, a1.w));
+        if (ok[u]) { ap[0] = make_float4(0.f, 0.f, 0.f, 0.f); ap[1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      } else {
+        graw[u] = *reinterpret_cast<const uint4*>(dqkv + off);
+      }
       xraw[u] = __ldg(reinterpret_cast<const uint4*>(qkv_raw + off));
       st[u] = __ldg(reinterpret_cast<const float2*>(stats + static_cast<size_t>(v) * 2));
     }
@@ -332,15 +343,15 @@ void qkln_rope_fwd(const void* qkv, const float* qg, const float* kg, const floa
   check_launch("qkln_rope_fwd");
 }
 void qkln_rope_bwd(void* dqkv, const void* qkv_raw, const float* stats, const float* qg, const float* kg, const float* sin_t,
-                   const float* cos_t, float* dqg, float* dkg, long long M, int T, int H, int C, int num_sms, cudaStream_t s) {
+                   const float* cos_t, float* dqg, float* dkg, long long M, int T, int H, int C, int num_sms, cudaStream_t s, float* dq_acc) {
   const long long nvec64 = M * 2 * H;
   if (nvec64 >= (1ll << 31)) throw std::runtime_error("qkln_rope: too many (token, head) vectors for 32-bit indexing");
   const unsigned nvec = static_cast<unsigned>(nvec64);
   const unsigned grid = static_cast<unsigned>(num_sms * 4);
   if (C == 64)
-    qkln_rope_bwd_kernel<64, 4><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
+    qkln_rope_bwd_kernel<64, 4><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H, dq_acc);
   else if (C == 128)
-    qkln_rope_bwd_kernel<128, 4><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H);
+    qkln_rope_bwd_kernel<128, 4><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(qkv_raw), stats, qg, kg, sin_t, cos_t, dqg, dkg, nvec, T, H, dq_acc);
   else throw std::runtime_error("qkln_rope: head_dim must be 64 or 128");
   check_launch("qkln_rope_bwd");
 }

@@ -42,6 +42,9 @@ class EngineConfig:
     micro_batch_size: int = 0      # sequences per GPU per micro-step; 0 = choose automatically
     gather_mode: str = "auto"      # "step" (bf16 weights resident all step) | "layer" (gather per layer, free after use)
     prefetch_depth: int = 2        # units gathered ahead of the consumer when gather_mode == "layer"
+    grad_shard: bool = False       # True: reduce-scatter every unit's gradients EVERY micro-step into a shard-sized fp32 accumulator
+                                   # (ZeRO-2/3 gradient memory, the reference's behaviour, src/train.py:87); False: accumulate locally
+                                   # in full size and reduce-scatter once per step (less traffic; 4 bytes/param extra per GPU)
     fp8: bool = False              # forward GEMMs of the blocks in e4m3 on the fp8 tensor cores; backward stays bf16
     fp8_format: str = "mx"         # "mx": OCP MX block scaling (UE8M0 per 32 elements, tcgen05 block_scale) | "row": one fp32 scale per row
     seed: int = 0

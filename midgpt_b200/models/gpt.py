@@ -124,7 +124,8 @@ class GPTModel:
         dproj = dx2 if p == 0.0 else be.dropout(dx2, p, _site_seed(step_seed, micro, layer, 2))
         be.linear_wgrad(dproj, s["o"], g["attn_proj"])
         do = be.linear_dgrad(dproj, w["attn_proj"])
-        dqkv = be.attention_bwd(do, s["qkv"], s["o"], s["lse"], B, T, H, C, p, _site_seed(step_seed, micro, layer, 1))
+        # fuse_dq: dq stays in the kernel's fp32 accumulator and is consumed (and cleared) by qkln_rope_bwd right below
+        dqkv = be.attention_bwd(do, s["qkv"], s["o"], s["lse"], B, T, H, C, p, _site_seed(step_seed, micro, layer, 1), fuse_dq=True)
         dqkv_raw = be.qkln_rope_bwd(dqkv, s["qkv_raw"], s["stats"], w["q_ln"], w["k_ln"],
                                     g["q_ln"], g["k_ln"], B, T, H, C)
         be.linear_wgrad(dqkv_raw, s["h1"], g["c_attn"])

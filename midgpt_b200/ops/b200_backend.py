@@ -61,6 +61,7 @@ class B200Backend:
         self._torch = TorchBackend(use_aten_flash=False)
         self._rope: tp.Dict[tp.Tuple[int, int], tp.Tuple[torch.Tensor, torch.Tensor]] = {}
         self._logits_ws: torch.Tensor | None = None
+        self._dq_acc: tp.Dict[tp.Tuple[int, int], torch.Tensor] = {}
         self.launches = 0          # kernels launched through this backend (bench.py reports it)
         self.carried = 0           # GEMM launches that carried an FSDP unit's all-gather (all-gather ⊕ GEMM)
 
@@ -186,8 +187,22 @@ class B200Backend:
     def qkln_rope_bwd(self, dqkv, qkv_raw, stats, q_gain, k_gain, dq_gain_acc, dk_gain_acc, B, T, H, C):
         sin, cos = self._rope_tables(C, T)
         self.launches += 1
-        self.ext.qkln_rope_bwd(dqkv, qkv_raw, stats, q_gain.float(), k_gain.float(), sin, cos, dq_gain_acc, dk_gain_acc, T, H, C)
+        # dq may still sit in the attention backward's fp32 accumulator (see attention_bwd): read it from there and clear it
+        acc = getattr(dqkv, "_mg_dq_acc", None)
+        self.ext.qkln_rope_bwd(dqkv, qkv_raw, stats, q_gain.float(), k_gain.float(), sin, cos, dq_gain_acc, dk_gain_acc, T, H, C, acc)
+        if acc is not None:
+            dqkv._mg_dq_acc = None
         return dqkv
+
+    def _dq_accumulator(self, M: int, D: int) -> torch.Tensor:
+        """A persistent, all-zero fp32 [M, D] buffer for the attention backward's dQ partial sums.  Invariant: zero between uses
+        (qkln_rope_bwd clears what it reads), so no per-layer zero-fill kernel is launched."""
+        key = (M, D)
+        buf = self._dq_acc.get(key)
+        if buf is None:
+            buf = torch.zeros((M, D), dtype=torch.float32, device=self.device)
+            self._dq_acc[key] = buf
+        return buf
 
     # ---------------------------------------------------------------- attention
     @staticmethod
@@ -203,10 +218,19 @@ class B200Backend:
         o, lse = self.ext.attn_fwd(q, k, v, float(dropout_p), int(seed) & 0x7FFFFFFFFFFFFFFF)
         return o, lse
 
-    def attention_bwd(self, do, h: QKV, o, lse, B, T, H, C, dropout_p=0.0, seed=0):
+    def attention_bwd(self, do, h: QKV, o, lse, B, T, H, C, dropout_p=0.0, seed=0, fuse_dq: bool = False):
+        """Returns dqkv [M, 3D] (dq | dk | dv).  With ``fuse_dq`` the dq third is NOT materialised: dq stays in the fp32
+        accumulator the kernel reduce-adds into, tagged onto the result for ``qkln_rope_bwd`` (its only consumer in the model),
+        which saves the zero-fill and the fp32->bf16 conversion pass per layer."""
         q, k, v = self._views(h, B, T, H, C)
-        self.launches += 3
-        return self.ext.attn_bwd(q, k, v, o, do.contiguous(), lse, float(dropout_p), int(seed) & 0x7FFFFFFFFFFFFFFF)
+        if not fuse_dq:
+            self.launches += 4          # prep, zero-fill, kernel, convert
+            return self.ext.attn_bwd(q, k, v, o, do.contiguous(), lse, float(dropout_p), int(seed) & 0x7FFFFFFFFFFFFFFF, None)
+        acc = self._dq_accumulator(B * T, H * C)
+        self.launches += 2
+        dqkv = self.ext.attn_bwd(q, k, v, o, do.contiguous(), lse, float(dropout_p), int(seed) & 0x7FFFFFFFFFFFFFFF, acc)
+        dqkv._mg_dq_acc = acc
+        return dqkv
 
     # ---------------------------------------------------------------- LM head + cross-entropy
     def _logits_buf(self, rows: int, vpad: int) -> torch.Tensor:

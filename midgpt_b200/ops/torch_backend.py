@@ -181,7 +181,7 @@ class TorchBackend:
         o = (p @ v).permute(0, 2, 1, 3).reshape(B * T, H * C)
         return o, lse
 
-    def attention_bwd(self, do, qkv, o, lse, B, T, H, C, dropout_p=0.0, seed=0):
+    def attention_bwd(self, do, qkv, o, lse, B, T, H, C, dropout_p=0.0, seed=0, fuse_dq: bool = False):
         x = qkv.view(B, T, 3, H, C)
         if self.use_aten_flash and qkv.is_cuda and dropout_p == 0.0 and qkv.dtype in (torch.bfloat16, torch.float16):
             q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))

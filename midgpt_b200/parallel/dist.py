@@ -62,13 +62,18 @@ def init_distributed(device_type: str | None = None) -> tp.Tuple[int, int, int, 
 
 
 def make_mesh(shard_model: bool, device_type: str | None = None, max_shard: int = 8) -> Mesh:
-    """shard group = min(world, 8) consecutive ranks when ``shard_model`` else 1 (pure DP).
+    """shard group = the ranks of ONE NODE (``LOCAL_WORLD_SIZE`` consecutive ranks, at most 8) when ``shard_model`` else 1
+    (pure DP); replica groups run across nodes (HSDP).
 
-    The reference hard-codes 8 (``n_devices // 8``, src/train.py:129-130) and therefore cannot run on
-    1/2/4 devices; here the group shrinks with the world.
+    The reference hard-codes 8 (``n_devices // 8``, src/train.py:129-130) and therefore cannot run on 1/2/4 devices; here the
+    group is the NVLink domain the launcher reports: parameters are sharded where peer memory / NVSwitch multicast exist (the
+    in-kernel collectives need it) and replicated across nodes, where only NCCL all-reduces of shard-sized gradients travel.
     """
     rank, world, local_rank, device, backend = init_distributed(device_type)
-    S = min(world, max_shard) if shard_model else 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if local_world < 1 or world % local_world:
+        local_world = world
+    S = min(world, max_shard, local_world) if shard_model else 1
     while world % S:
         S -= 1
     R = world // S

@@ -79,6 +79,8 @@ class FSDPEngine:
             self.comm = "fused" if fused_ok else (mesh.backend if mesh.backend != "none" else "none")
         self.comm_stream = torch.cuda.Stream(self.device) if self.cuda else None
         self.fused = None                                # parallel.fused.FusedComm when comm == "fused"
+        # ZeRO-2/3 gradient memory: reduce-scatter every unit every micro-step, keep only a shard-sized fp32 accumulator
+        self.grad_sharded = bool(cfg.engine.grad_shard) and self.S > 1
 
         specs = P.build_unit_specs(cfg.model_config)
         self.units: tp.List[ShardedUnit] = []
@@ -88,14 +90,25 @@ class FSDPEngine:
             full32 = P.init_unit_flat(spec, cfg.model_config, seed, padded)          # CPU, deterministic
             master = full32[self.sr * shard:(self.sr + 1) * shard].to(self.device, self.param_dtype).contiguous()
             del full32
-            grad_full = torch.zeros(padded, dtype=torch.float32, device=self.device)
-            grad_shard = grad_full if self.S == 1 else torch.zeros(shard, dtype=torch.float32, device=self.device)
+            if self.grad_sharded:      # full-size fp32 buffers exist only in a small rotating pool (see _grad_buffer)
+                grad_full = None
+                grad_shard = torch.zeros(shard, dtype=torch.float32, device=self.device)
+            else:
+                grad_full = torch.zeros(padded, dtype=torch.float32, device=self.device)
+                grad_shard = grad_full if self.S == 1 else torch.zeros(shard, dtype=torch.float32, device=self.device)
             u = ShardedUnit(spec, padded, shard, master,
                             torch.zeros(shard, dtype=torch.float32, device=self.device),
                             torch.zeros(shard, dtype=torch.float32, device=self.device),
                             grad_full, grad_shard, None, None)
             self.units.append(u)
         self._alloc_lp()
+        if self.grad_sharded:
+            big = max(u.padded for u in self.units)
+            self._gpool = [torch.zeros(big, dtype=torch.float32, device=self.device) for _ in range(3)]
+            self._gpool_free = [0, 1, 2]
+            self._gpool_ready: tp.List[tp.Any] = [None, None, None]     # event: the buffer's last reduction has finished (and zeroed it)
+            self._gslot: tp.Dict[int, int] = {}                         # unit -> pool buffer while its backward is in flight
+            self._gtmp = torch.empty(big // self.S, dtype=torch.float32, device=self.device) if True else None
         self._need_gather = True
         self._micro_is_last = True
         self._pending_reduce: tp.List[int] = []
@@ -269,14 +282,62 @@ class FSDPEngine:
             # the pointer would silently be another layer's weights
             self.be.notify_weights_updated()
 
+    def _grad_buffer(self, unit: int) -> torch.Tensor:
+        """Sharded-gradient mode: the full-size fp32 buffer this unit's backward accumulates into during ONE micro-step."""
+        k = self._gslot.get(unit)
+        if k is None:
+            if not self._gpool_free:
+                raise RuntimeError("gradient pool exhausted: more than 3 units have un-reduced gradients")
+            k = self._gpool_free.pop(0)
+            self._gslot[unit] = k
+            if self.cuda and self._gpool_ready[k] is not None:
+                torch.cuda.current_stream().wait_event(self._gpool_ready[k])     # its previous reduction has zeroed it
+        return self._gpool[k][: self.units[unit].padded]
+
     def grads(self, unit: int) -> tp.Dict[str, torch.Tensor]:
         u = self.units[unit]
-        return P.unit_views(u.spec, u.grad_full)
+        return P.unit_views(u.spec, self._grad_buffer(unit) if self.grad_sharded else u.grad_full)
 
     def grads_ready(self, unit: int) -> None:
+        if self.grad_sharded:
+            self._reduce_unit_sharded(unit)
+            return
         if not self._micro_is_last:
             return
         self._reduce_unit(unit)
+
+    def _reduce_unit_sharded(self, i: int) -> None:
+        """Every micro-step: reduce-scatter the unit's pool buffer, ADD the result to the shard-sized accumulator, zero the buffer
+        and hand it back (reference: grads are constrained to the parameter sharding inside every micro-step, src/train.py:87)."""
+        u, m = self.units[i], self.mesh
+        k = self._gslot.pop(i)
+        buf = self._gpool[k][: u.padded]
+
+        def work():
+            if self.fused is not None:
+                self.fused.reduce_scatter_accumulate(u, k, self._micro_is_last and m.replica_size == 1)
+            else:
+                tmp = self._gtmp[: u.shard]
+                D.reduce_scatter_avg(tmp, buf, m.shard_group, m.backend)
+                u.grad_shard.add_(tmp)
+                buf.zero_()
+            if m.replica_size > 1 and self._micro_is_last:
+                D.all_reduce_avg(u.grad_shard, m.replica_group, m.backend)
+
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                work()
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+            self._gpool_ready[k] = done
+            if self._micro_is_last:
+                u.reduced_event = done
+        else:
+            work()
+        self._gpool_free.append(k)
 
     # ------------------------------------------------------------------ gradient reduction
     def _reduce_unit(self, i: int) -> None:
@@ -384,7 +445,7 @@ class FSDPEngine:
                 be.adamw_step(u.master, u.exp_avg, u.exp_avg_sq, u.grad_shard, u.lp_shard,
                               lr=sc.lr, b1=sc.b1, b2=sc.b2, eps=sc.eps, wd_over_lr_peak=sc.wd_over_lr_peak,
                               bc1=sc.bc1, bc2=sc.bc2, grad_scale=clip)
-                u.grad_full.zero_()
+                (u.grad_shard if self.grad_sharded else u.grad_full).zero_()
         if self.cuda:
             self._opt_done_event = torch.cuda.Event()
             self._opt_done_event.record(torch.cuda.current_stream())
@@ -460,7 +521,7 @@ class FSDPEngine:
         return {
             "master_GB": n * self.units[0].master.element_size() * gb,
             "adam_GB": n * 8 * gb,
-            "grad_full_GB": sum(u.padded for u in self.units) * 4 * gb,
+            "grad_full_GB": (3 * max(u.padded for u in self.units) + n if self.grad_sharded else sum(u.padded for u in self.units)) * 4 * gb,
             "lp_resident_GB": (sum(u.padded for u in self.units) if self.gather_mode == "step"
                                else sum(u.shard for u in self.units)) * 2 * gb,
         }

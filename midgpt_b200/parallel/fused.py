@@ -55,7 +55,10 @@ class FusedComm:
         group = mesh.shard_group
         dev = engine.device
         total = sum(u.padded for u in engine.units)
-        self.grad_arena = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        # gradient accumulators peers pull from: every unit in full size, or (sharded-gradient mode) the 3 rotating pool buffers
+        self.grad_sharded = engine.grad_sharded
+        gbig = max(u.padded for u in engine.units)
+        self.grad_arena = symm_mem.empty(3 * gbig if self.grad_sharded else total, dtype=torch.float32, device=dev)
         # step mode: every rank holds the full gathered weights (peers push into it).  layer mode: only the local
         # shards are symmetric (peers pull from them inside the consuming GEMM) and gathered copies live in a local pool.
         lp_elems = total // self.world if self.layer_mode else total
@@ -82,7 +85,8 @@ class FusedComm:
         for i, u in enumerate(engine.units):
             self.offsets[i] = off
             self.shard_offsets[i] = soff
-            u.grad_full = self.grad_arena[off:off + u.padded]
+            if not self.grad_sharded:
+                u.grad_full = self.grad_arena[off:off + u.padded]
             if self.layer_mode:
                 u.lp_shard = self.lp_arena[soff:soff + u.shard]
             else:
@@ -97,6 +101,9 @@ class FusedComm:
             self.slot_flags = [torch.zeros(n_seg, dtype=torch.int32, device=dev) for _ in range(n_slots)]
             self.slot_calls = [0] * n_slots
             self._scratch_flags = torch.zeros(8, dtype=torch.int32, device=dev)     # stand-alone pulls are ordered by the stream
+        if self.grad_sharded:
+            self.gbig = gbig
+            engine._gpool = [self.grad_arena[k * gbig:(k + 1) * gbig] for k in range(3)]
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._pushed = False
         self.stats = {"xrank_barrier": 0, "rs_sumsq": 0, "adamw_allgather": 0, "ag_pull": 0, "gemm_ag": 0}
@@ -141,16 +148,28 @@ class FusedComm:
         i = self.e.units.index(u)
         self._barrier()                                   # every rank finished accumulating this unit
         off = self.offsets[i] + self.rank * u.shard
-        self.ext.rs_sumsq(self.grad_ptrs, self.mc_grad, u.grad_shard, self.sumsq, off, self.rank)
+        self.ext.rs_sumsq(self.grad_ptrs, self.mc_grad, u.grad_shard, self.sumsq, off, self.rank, False, True)
         self.stats["rs_sumsq"] += 1
+
+    def reduce_scatter_accumulate(self, u, k: int, want_sumsq: bool) -> None:
+        """Sharded-gradient mode, comm stream, every micro-step: pull this rank's shard of pool buffer k from every peer, ADD the
+        mean to the fp32 shard accumulator (Σg² of the final value on the last micro-step), then zero the local buffer once every
+        peer has pulled from it."""
+        self._barrier()                                   # every rank finished this unit's backward of this micro-step
+        off = k * self.gbig + self.rank * u.shard
+        self.ext.rs_sumsq(self.grad_ptrs, self.mc_grad, u.grad_shard, self.sumsq, off, self.rank, True, want_sumsq)
+        self.stats["rs_sumsq"] += 1
+        self._barrier()                                   # every rank has pulled: the buffer may be cleared and reused
+        self.grad_arena[k * self.gbig:k * self.gbig + u.padded].zero_()
 
     def optimizer_step(self) -> torch.Tensor:
         """Runs on the engine's compute stream after all reduce events have been waited on."""
         e = self.e
-        ev0 = e._mark()
-        self._barrier()                                   # all pulls everywhere are done -> accumulators reusable
-        e._exposed(ev0)
-        self.grad_arena.zero_()
+        if not self.grad_sharded:
+            ev0 = e._mark()
+            self._barrier()                               # all pulls everywhere are done -> accumulators reusable
+            e._exposed(ev0)
+            self.grad_arena.zero_()
         if e.mesh.replica_size > 1:
             # HSDP: rs_sumsq accumulated Σg² of the *intra-node* mean, before the replica all-reduce changed grad_shard;
             # every replica group would otherwise clip with its own norm and the replicas' weights would drift apart.
@@ -175,6 +194,9 @@ class FusedComm:
             self.ext.adamw_allgather(u.master, u.exp_avg, u.exp_avg_sq, u.grad_shard, self.lp_ptrs, self.mc_lp, off, clip1,
                                      sc.lr, sc.b1, sc.b2, sc.eps, sc.wd_over_lr_peak, sc.bc1, sc.bc2)
             self.stats["adamw_allgather"] += 1
+        if self.grad_sharded:
+            for u in e.units:
+                u.grad_shard.zero_()                      # shard-sized accumulators of the next step
         ev0 = e._mark()
         self._barrier()                                   # every rank's pushes have landed everywhere
         e._exposed(ev0)

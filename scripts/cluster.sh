@@ -7,7 +7,10 @@
 #   gpu list | ips | check | df               inspect nodes (nvidia-smi, tmux pane of the run, disk)
 #   gpu ssh '<cmd>'                           run a command on every node (fan-out, waits for all)
 #   gpu copy                                  rsync this repo to ~/midgpt_b200 on every node
-#   gpu setup                                 build the native extensions on every node (no pip/network needed)
+#   gpu setup [dataset_dir]                   scripts/setup_node.sh on every node: verify driver/torch/NVLink, build the sm_100a
+#                                             extensions, link the dataset at /mnt/disks/persist, run the smoke (reference: setup.sh)
+#   gpu health                                ECC / throttle / NVLink error counters of every GPU on every node
+#   gpu reboot                                reboot every node (reference: tpu reboot)
 #   gpu launch <config> <rundir> [flags…]     start training in a detached tmux session on every node (torchrun, 8 ranks/node)
 #   gpu stop                                  kill the tmux session and the exact torchrun process group on every node
 #   gpu maintain <host>                       fault injection: SIGKILL one rank on <host> (run then resumes from the last checkpoint)
@@ -28,7 +31,9 @@ gpu() {
     df)     _gpu_each "df -h . | tail -1" ;;
     ssh)    _gpu_each "$*" ;;
     copy)   for h in ${hosts[@]}; do rsync -az --delete --exclude .git --exclude outputs --exclude gpurun_out ./ $h:$GPU_REPO_DIR/ & done; wait ;;
-    setup)  _gpu_each "cd $GPU_REPO_DIR && python -m midgpt_b200.ops.build" ;;
+    setup)  _gpu_each "cd $GPU_REPO_DIR && bash scripts/setup_node.sh $1" ;;
+    health) _gpu_each "nvidia-smi --query-gpu=index,ecc.errors.uncorrected.volatile.total,clocks_event_reasons.hw_slowdown,temperature.gpu,power.draw --format=csv,noheader; nvidia-smi nvlink -e 2>/dev/null | grep -ci error | xargs -I{} echo 'nvlink error lines: {}'" ;;
+    reboot) _gpu_each "sudo reboot" ;;
     check)  _gpu_each "tmux capture-pane -pt midgpt 2>/dev/null | tail -n 5 || echo 'no session'" ;;
     launch)
       local config=$1 rundir=$2; shift 2
@@ -45,6 +50,6 @@ gpu() {
       local config=$1 rundir=$2; shift 2
       until gpu launch $config $rundir "$@" && gpu wait; do echo "run failed — relaunching in 30 s (resumes from the last checkpoint)"; gpu stop; sleep 30; done ;;
     wait)   while _gpu_each "tmux has-session -t midgpt 2>/dev/null && echo alive" | grep -q alive; do sleep 20; done ;;
-    *) echo "usage: gpu {list|ips|df|ssh|copy|setup|check|launch|stop|maintain|retry_launch|wait}" ;;
+    *) echo "usage: gpu {list|ips|df|ssh|copy|setup|health|reboot|check|launch|stop|maintain|retry_launch|wait}" ;;
   esac
 }

@@ -1,10 +1,12 @@
 #!/bin/bash
-# compute-sanitizer targets for the hand-written kernels (the reference has no race detection at all).
-#   bash scripts/sanitize.sh [memcheck|racecheck|synccheck|initcheck]     (run on a GPU box, e.g. under gpurun)
-TOOL=${1:-memcheck}
+# compute-sanitizer over every hand-written kernel family (the reference has no race detection at all).
+#   bash scripts/sanitize.sh [memcheck|racecheck|synccheck|initcheck] ...     (run on a GPU box, e.g. under gpurun)
+# Targets: tests/sanitize_targets.py (tiny shapes: pair / single-CTA / fp8 / MX GEMMs with every epilogue incl. split-K wgrad,
+# attention forward + backward v3 + v2-with-dropout for both head dims, element-wise, cross-entropy, optimizer).
 mkdir -p gpurun_out
-timeout ${SAN_TMO:-1500} compute-sanitizer --tool $TOOL --error-exitcode 1 \
-  python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "gemm_nt or rmsnorm or qkln or embedding or adamw or attention" -p no:cacheprovider \
-  > gpurun_out/sanitize_$TOOL.log 2>&1
-echo "compute-sanitizer $TOOL exit $?"
-tail -n 15 gpurun_out/sanitize_$TOOL.log
+for TOOL in "${@:-memcheck}"; do
+  timeout ${SAN_TMO:-900} compute-sanitizer --tool $TOOL --error-exitcode 1 \
+    python -m pytest tests/sanitize_targets.py -q -m gpu -p no:cacheprovider > gpurun_out/sanitize_$TOOL.log 2>&1
+  echo "compute-sanitizer $TOOL exit $?"
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|passed|failed|Error" gpurun_out/sanitize_$TOOL.log | tail -n 8
+done

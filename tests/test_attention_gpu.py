@@ -133,3 +133,25 @@ def test_attention_dropout_in_kernel(be, B, T, H, C):
     o0, _ = be.attention_fwd(h, B, T, H, C, 0.0, seed)
     o0_r, _ = ref_attention(q, k, v)
     assert row_err(o0, o0_r) < 1.5e-2
+
+
+@pytest.mark.parametrize("B,T,H,C", [(2, 512, 3, 64), (2, 256, 2, 128)])
+def test_fused_dq_path_equals_unfused(be, B, T, H, C):
+    """Model path: dq stays in the backward's fp32 accumulator, qkln_rope_bwd reads it there and clears it -- no zero-fill, no
+    fp32->bf16 conversion kernel.  Must equal the unfused pipeline bit for bit and leave the accumulator all-zero."""
+    h, q, k, v = make_inputs(B, T, H, C, 21)
+    D = H * C
+    o, lse = be.attention_fwd(h, B, T, H, C)
+    do = rnd(B * T, D)
+    gq, gk = torch.rand(C, device="cuda") + 0.5, torch.rand(C, device="cuda") + 0.5
+    _, stats = be.qkln_rope_fwd(h.raw, gq, gk, B, T, H, C)
+    outs = []
+    for fuse in (False, True, True):            # twice fused: the accumulator must be reusable
+        dgq, dgk = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        dqkv = be.attention_bwd(do, h, o, lse, B, T, H, C, fuse_dq=fuse)
+        out = be.qkln_rope_bwd(dqkv, h.raw, stats, gq, gk, dgq, dgk, B, T, H, C)
+        outs.append((out.clone(), dgq, dgk))
+    for got in outs[1:]:
+        assert torch.equal(got[0], outs[0][0])
+        assert torch.allclose(got[1], outs[0][1], rtol=1e-4, atol=1e-4) and torch.allclose(got[2], outs[0][2], rtol=1e-4, atol=1e-4)
+    assert be._dq_accumulator(B * T, D).abs().max().item() == 0.0

@@ -26,10 +26,11 @@ def _batches(cfg, n_steps):
              torch.randint(0, 65, (N, T), generator=g, dtype=torch.int32)) for _ in range(n_steps)]
 
 
-def _run(rank, world, shard_model, gather_mode, n_steps):
+def _run(rank, world, shard_model, gather_mode, n_steps, grad_shard=False):
     from midgpt_b200.train import Trainer
     torch.manual_seed(0)
     cfg = _tiny_cfg(shard_model, gather_mode)
+    cfg.engine.grad_shard = grad_shard
     tr = Trainer(cfg, device_type="cpu")
     losses = []
     for x, y in _batches(cfg, n_steps):
@@ -39,14 +40,20 @@ def _run(rank, world, shard_model, gather_mode, n_steps):
         ys = y.view(G, B, T)[:, rank * B // world:(rank + 1) * B // world].reshape(-1, T)
         losses.append(tr.train_step(xs, ys).item())
     state = {k: v.clone() for k, v in tr.engine.full_state("master").items()}
+    if grad_shard and world > 1:       # ZeRO-2/3 gradient memory: no full-size accumulator exists
+        assert all(u.grad_full is None for u in tr.engine.units)
+        assert tr.engine.memory_report()["grad_full_GB"] < 4 * sum(u.padded for u in tr.engine.units) * 4 / 2 ** 30
     return losses, state, tr.engine.last_grad_norm.item()
 
 
-@pytest.mark.parametrize("shard_model,gather_mode", [(True, "step"), (True, "layer"), (False, "step")])
-def test_fsdp_ws2_equals_single(shard_model, gather_mode):
+@pytest.mark.parametrize("shard_model,gather_mode,grad_shard", [(True, "step", False), (True, "layer", False), (False, "step", False),
+                                                              (True, "layer", True), (True, "step", True)])
+def test_fsdp_ws2_equals_single(shard_model, gather_mode, grad_shard):
+    """grad_shard=True: gradients are reduce-scattered every micro-step (g_accum = 2 x 2 micro-batches here) into a shard-sized
+    accumulator -- the reference's per-microstep sharding constraint (src/train.py:87)."""
     n_steps = 4
     ref_losses, ref_state, ref_gn = _run(0, 1, False, "step", n_steps)
-    outs = run_distributed(_run, 2, shard_model, gather_mode, n_steps)
+    outs = run_distributed(_run, 2, shard_model, gather_mode, n_steps, grad_shard)
     for losses, state, gn in outs:
         assert torch.allclose(torch.tensor(losses), torch.tensor(ref_losses), rtol=1e-5, atol=1e-6)
         assert abs(gn - ref_gn) < 1e-4 * max(1.0, ref_gn)

@@ -8,7 +8,7 @@ from tests._mp import run_distributed
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 
-def _cfg(comm, gather_mode="step", shard=True):
+def _cfg(comm, gather_mode="step", shard=True, grad_shard=False):
     from midgpt_b200 import load_config
     from midgpt_b200.config import GPTConfig
     cfg = load_config("shakespeare_char")
@@ -17,13 +17,14 @@ def _cfg(comm, gather_mode="step", shard=True):
     cfg.warmup_steps, cfg.lr_decay_steps, cfg.max_steps = 2, 50, 50
     cfg.engine.backend, cfg.engine.comm, cfg.engine.micro_batch_size = "b200", comm, 2
     cfg.engine.gather_mode = gather_mode
+    cfg.engine.grad_shard = grad_shard
     return cfg
 
 
-def _run(rank, world, comm, gather_mode, steps):
+def _run(rank, world, comm, gather_mode, steps, grad_shard=False):
     from midgpt_b200.train import Trainer
     torch.cuda.set_device(rank)
-    tr = Trainer(_cfg(comm, gather_mode), device_type="cuda")
+    tr = Trainer(_cfg(comm, gather_mode, grad_shard=grad_shard), device_type="cuda")
     g = torch.Generator().manual_seed(7)
     losses = []
     for _ in range(steps):
@@ -35,8 +36,8 @@ def _run(rank, world, comm, gather_mode, steps):
     return losses, {k: v.float().cpu() for k, v in state.items()}, tr.engine.last_grad_norm.item()
 
 
-@pytest.mark.parametrize("gather_mode", ["step", "layer"])
-def test_fused_comm_matches_nccl(gather_mode):
+@pytest.mark.parametrize("gather_mode,grad_shard", [("step", False), ("layer", False), ("layer", True)])
+def test_fused_comm_matches_nccl(gather_mode, grad_shard):
     """step: rs_sumsq pull + adamw_allgather push;  layer: rs_sumsq pull + all-gather ⊕ GEMM (csrc/gemm.cu gather path)."""
     world = min(torch.cuda.device_count(), 8)
     if world < 2:
@@ -44,7 +45,7 @@ def test_fused_comm_matches_nccl(gather_mode):
     world = 2 if world < 4 else world
     steps = 5
     nccl = run_distributed(_run, world, "nccl", "step", steps, timeout=600)
-    fused = run_distributed(_run, world, "fused", gather_mode, steps, timeout=600)
+    fused = run_distributed(_run, world, "fused", gather_mode, steps, grad_shard, timeout=600)
     for r in range(world):
         ln, sn, gn = nccl[r]
         lf, sf, gf = fused[r]
