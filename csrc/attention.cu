@@ -103,7 +103,9 @@ template <int C, bool DROP>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
-                int T, int H, float scale, uint32_t thr16, float inv_keep, uint2 seed) {
+                int T, int H, float scale, uint32_t thr16, float inv_keep, uint2 seed, int eager) {
+  // eager (MIDGPT_ATTN_DEBUG & 8, for compute-sanitizer synccheck only): await every phase of pv_done.  By design the softmax warps
+  // await that barrier lazily, so phases complete that nobody waits for -- which synccheck reports as "missing wait" and aborts.
   using Cfg = FwdCfg<C>;
   constexpr int BQ = Cfg::BQ, BKV = Cfg::BKV;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -207,8 +209,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int k = 0; k < BKV / 16; ++k)       // A = P_j straight from TMEM: 16 keys = 8 packed columns per k-step
             umma_bf16_ts(tmem + Cfg::O_COL, tmem + Cfg::S_COL + st * BKV + k * 8, desc_shift(v_desc, k * 2048), idesc_o, (j | k) != 0);
           umma_commit(&v_empty[st]);
-          umma_commit(pv_done);
-          if (j + 1 == n_kv) umma_commit(o_done);
+          if (j + 1 < n_kv) umma_commit(pv_done);   // (the last P·V is awaited through o_done only)
+          else umma_commit(o_done);
         }
         __syncwarp();
         if (j + 2 < n_kv) issue_qk(j + 2);   // reuses S buffer j&1, which the softmax warps released at p_full(j)
@@ -265,7 +267,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mx *= sl2;                                             // sl2 > 0: max commutes with the scaling
       if (j > 0) {
         const bool need = mx > m_used + 8.f;       // lazy rescale: only when the max grew by > 2^8
-        if (__any_sync(0xffffffffu, need)) {
+        if (__any_sync(0xffffffffu, need) || eager) {
           mbar_wait(pv_done, (j - 1) & 1);         // O_{j-1} complete (P_{j-1} lives in the other S buffer: nothing else to wait for)
           tc_fence_after();
           const float alpha = need ? exp2f(m_used - mx) : 1.f;
@@ -1255,7 +1257,8 @@ static void launch_fwd(const void* q, const void* k, const void* v, void* o, flo
               tv = make_tmap_bthc(v, B, T, H, C, v_row_stride, Cfg::BKV);
   static bool once = (set_smem(attn_fwd_kernel<C, DROP>, Cfg::SMEM), true);
   (void)once;
-  attn_fwd_kernel<C, DROP><<<grid, 192, Cfg::SMEM, s>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, T, H, scale, d.thr16, d.inv_keep, d.seed);
+  static const int eager = [] { const char* e = getenv("MIDGPT_ATTN_DEBUG"); return e ? (atoi(e) & 8) : 0; }();
+  attn_fwd_kernel<C, DROP><<<grid, 192, Cfg::SMEM, s>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, T, H, scale, d.thr16, d.inv_keep, d.seed, eager);
 }
 
 void attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, int C, long long q_row_stride,

@@ -43,8 +43,18 @@ def _entry(rank, world, port, fn, args, q):
             pass
 
 
-def run_distributed(fn, world: int, *args, timeout: float = 240.0):
-    """Run ``fn(rank, world, *args)`` in ``world`` processes; returns the list of return values by rank."""
+def run_distributed(fn, world: int, *args, timeout: float = 240.0, _retries: int = 2):
+    """Run ``fn(rank, world, *args)`` in ``world`` processes; returns the list of return values by rank.  A rendezvous port
+    that got taken between probing and binding (EADDRINUSE) is retried with a fresh port."""
+    try:
+        return _run_once(fn, world, args, timeout)
+    except RuntimeError as e:
+        if _retries > 0 and ("EADDRINUSE" in str(e) or "address already in use" in str(e)):
+            return run_distributed(fn, world, *args, timeout=timeout, _retries=_retries - 1)
+        raise
+
+
+def _run_once(fn, world: int, args, timeout: float):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
