@@ -58,8 +58,32 @@ def gemm_epilogue_bench(be, dev, flush, peak):
                               "frac_of_cublas_peak": round(fl / (t * 1e-3) / peak, 3)}), flush=True)
 
 
+def dq_fuse_bench(be, dev, flush):
+    """attention backward + QK-LN/RoPE backward: dq through bf16 (zero-fill + kernel + convert + qkln) vs dq left in the fp32
+    accumulator and consumed by qkln_rope_bwd."""
+    r = lambda *s: torch.randn(*s, device=dev, dtype=torch.bfloat16)
+    for (B, T, H, C) in [(32, 1024, 16, 128), (32, 1024, 12, 64)]:
+        D = H * C
+        h = QKV(r(B * T, 2 * D), r(B * T, 3 * D))
+        o, lse = be.attention_fwd(h, B, T, H, C)
+        do = r(B * T, D)
+        gq, gk = torch.ones(C, device=dev), torch.ones(C, device=dev)
+        _, stats = be.qkln_rope_fwd(h.raw, gq, gk, B, T, H, C)
+        dgq, dgk = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        res = {}
+        for fuse in (False, True):
+            def fn(fuse=fuse):
+                d = be.attention_bwd(do, h, o, lse, B, T, H, C, fuse_dq=fuse)
+                be.qkln_rope_bwd(d, h.raw, stats, gq, gk, dgq, dgk, B, T, H, C)
+            res["fused_ms" if fuse else "unfused_ms"] = round(timeit(fn, flush=flush), 4)
+        print(json.dumps({"kernel": "attn_bwd+qkln_bwd", "B": B, "T": T, "H": H, "C": C, **res}), flush=True)
+
+
 def main():
     quick = "--quick" in sys.argv
+    if "--dq-fuse" in sys.argv:
+        dev = torch.device("cuda", 0)
+        return dq_fuse_bench(B200Backend(dev), dev, torch.empty(256 << 20, dtype=torch.uint8, device=dev))
     if "--gemm-epi" in sys.argv:
         dev = torch.device("cuda", 0)
         peak, _ = peak_flops_per_gpu()

@@ -223,7 +223,10 @@ class B200Backend:
         accumulator the kernel reduce-adds into, tagged onto the result for ``qkln_rope_bwd`` (its only consumer in the model),
         which saves the zero-fill and the fp32->bf16 conversion pass per layer."""
         q, k, v = self._views(h, B, T, H, C)
-        if not fuse_dq:
+        # measured (bench/kernel_bench.py --dq-fuse, backward + QK-LN/RoPE backward): head_dim 64: 0.419 -> 0.398 ms fused;
+        # head_dim 128: 0.809 -> 0.834 ms (the register-bound qkln kernel pays more for the fp32 read than the two small
+        # streaming kernels cost), so the fused hand-over is used where it wins
+        if not fuse_dq or C != 64:
             self.launches += 4          # prep, zero-fill, kernel, convert
             return self.ext.attn_bwd(q, k, v, o, do.contiguous(), lse, float(dropout_p), int(seed) & 0x7FFFFFFFFFFFFFFF, None)
         acc = self._dq_accumulator(B * T, H * C)
