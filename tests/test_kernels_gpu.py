@@ -254,3 +254,34 @@ def test_mxfp8_block_scaled_gemm(be, M, N, K):
     assert rel_err(be8.linear_fwd(x, w, res=res), ref + res.float()) < 6e-3
     pre, act = be8.linear_fwd(x, w, act="gelu")
     assert rel_err(pre, ref) < 6e-3 and rel_err(act, torch.nn.functional.gelu(pre.float(), approximate="tanh")) < 6e-3
+
+
+# ----------------------------------------------------------------------------------------------- GEMM at the models' real shapes
+@pytest.mark.parametrize("name,N,K", [("1.5B c_attn", 6144, 2048), ("1.5B mlp_proj", 2048, 8192), ("124M c_attn", 2304, 768),
+                                      ("124M mlp_proj", 768, 3072), ("124M c_fc", 3072, 768)])
+def test_gemm_model_shapes_rowwise(be, ref, name, N, K):
+    """Forward (+gelu / +residual), dgrad (+gelu') and wgrad on the layer shapes of both headline models at M = 8192 tokens, checked
+    per output row (max over rows of the relative row error) so that a mis-routed tile / box cannot hide in a Frobenius norm.
+    K = 768 exercises the TMA-box epilogue (5 operand stages), K >= 2048 the register epilogue (6 stages)."""
+    torch.manual_seed(5)
+    M = 8192
+    x, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+
+    def rows(a, b):
+        a, b = a.float(), b.float()
+        return ((a - b).norm(dim=1) / (b.norm(dim=1) + 1e-6)).max().item()
+
+    base = x.float() @ w.float().t()
+    assert rows(be.linear_fwd(x, w), base) < 8e-3
+    res = rnd(M, N)
+    assert rows(be.linear_fwd(x, w, res=res), base + res.float()) < 8e-3
+    pre, act = be.linear_fwd(x, w, act="gelu")
+    assert rows(pre, base) < 8e-3 and rows(act, torch.nn.functional.gelu(pre.float(), approximate="tanh")) < 8e-3
+    dy = rnd(M, N)
+    want = dy.float() @ w.float()
+    assert rows(be.linear_dgrad(dy, w), want) < 8e-3
+    gp = rnd(M, K)
+    assert rows(be.linear_dgrad(dy, w, gelu_pre=gp), ref.linear_dgrad(dy.float(), w.float(), gelu_pre=gp.float())) < 1.2e-2
+    acc = torch.zeros(N, K, device="cuda")
+    be.linear_wgrad(dy, x, acc)
+    assert rows(acc, dy.float().t() @ x.float()) < 4e-3
