@@ -21,9 +21,12 @@ def _cfg(comm, gather_mode="step", shard=True, grad_shard=False):
     return cfg
 
 
-def _run(rank, world, comm, gather_mode, steps, grad_shard=False):
+def _run(rank, world, comm, gather_mode, steps, grad_shard=False, local_world=0):
+    import os
     from midgpt_b200.train import Trainer
     torch.cuda.set_device(rank)
+    if local_world:                      # pretend the ranks live on world / local_world nodes: shard inside a "node", replicate across
+        os.environ["LOCAL_WORLD_SIZE"] = str(local_world)
     tr = Trainer(_cfg(comm, gather_mode, grad_shard=grad_shard), device_type="cuda")
     g = torch.Generator().manual_seed(7)
     losses = []
@@ -55,6 +58,28 @@ def test_fused_comm_matches_nccl(gather_mode, grad_shard):
             err = (torch.as_tensor(sf[k]) - torch.as_tensor(sn[k])).norm() / (torch.as_tensor(sn[k]).norm() + 1e-9)
             assert err < 2e-3, (k, err.item())
     assert nccl[0][0][-1] < nccl[0][0][0]
+
+
+def test_hsdp_fused_matches_nccl():
+    """4 GPUs as 2 "nodes" of 2: with the in-kernel path the clip norm must be taken AFTER the replica
+    all-reduce, otherwise every replica group clips with its own norm and the replicas' weights drift apart silently."""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    steps = 5
+    nccl = run_distributed(_run, 4, "nccl", "step", steps, False, 2, timeout=600)
+    fused = run_distributed(_run, 4, "fused", "step", steps, False, 2, timeout=600)
+    for r in range(4):
+        ln, sn, gn = nccl[r]
+        lf, sf, gf = fused[r]
+        assert max(abs(a - b) for a, b in zip(ln, lf)) < 2e-3, (ln, lf)
+        assert abs(gn - gf) < 1e-3 * max(1.0, gn), (gn, gf)
+        for k in sn:
+            err = (torch.as_tensor(sf[k]) - torch.as_tensor(sn[k])).norm() / (torch.as_tensor(sn[k]).norm() + 1e-9)
+            assert err < 2e-3, (k, err.item())
+    # replicas hold identical weights (rank 0 is in replica group 0, rank 2 in replica group 1, same shard rank)
+    for k in fused[0][1]:
+        assert torch.equal(torch.as_tensor(fused[0][1][k]), torch.as_tensor(fused[2][1][k])), k
+    assert nccl[0][2] > 1.0, "the test must exercise an active clip"
 
 
 def _flag_stress(rank, world, iters):
