@@ -439,6 +439,8 @@ class FSDPEngine:
                 sumsq = sumsq + be.sumsq(u.grad_shard).float()
             if self.S > 1:
                 D.all_reduce_sum(sumsq, self.mesh.shard_group)
+            if self.mesh.replica_size > 1:      # identical clip factor on every replica (Σg² uses order-dependent fp atomics on GPUs)
+                D.all_reduce_avg(sumsq, self.mesh.replica_group, self.mesh.backend)
             clip, gnorm = clip_factor_from_sumsq(sumsq)
             sc = step_scalars(self.count, self.cfg)
             for u in self.units:

@@ -181,6 +181,10 @@ class FusedComm:
         self.sumsq.zero_()
         ev0 = e._mark()
         dist.all_reduce(total, group=e.mesh.shard_group)   # 4 bytes
+        if e.mesh.replica_size > 1:
+            # Σg² is accumulated with floating-point atomics, whose order differs from GPU to GPU: without this (4-byte) average
+            # the replicas would clip with factors one ulp apart and their weights would drift away from each other bit by bit
+            dist.all_reduce(total, op=dist.ReduceOp.AVG, group=e.mesh.replica_group)
         e._exposed(ev0)
         clip, gnorm = clip_factor_from_sumsq(total[0])
         sc = step_scalars(e.count, e.cfg)

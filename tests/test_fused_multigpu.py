@@ -77,8 +77,10 @@ def test_hsdp_fused_matches_nccl():
             err = (torch.as_tensor(sf[k]) - torch.as_tensor(sn[k])).norm() / (torch.as_tensor(sn[k]).norm() + 1e-9)
             assert err < 2e-3, (k, err.item())
     # replicas hold identical weights (rank 0 is in replica group 0, rank 2 in replica group 1, same shard rank)
-    for k in fused[0][1]:
-        assert torch.equal(torch.as_tensor(fused[0][1][k]), torch.as_tensor(fused[2][1][k])), k
+    for name, runs in (("nccl", nccl), ("fused", fused)):
+        for k in runs[0][1]:
+            a, b = torch.as_tensor(runs[0][1][k]), torch.as_tensor(runs[2][1][k])
+            assert torch.equal(a, b), (name, k, (a - b).abs().max().item())
     assert nccl[0][2] > 1.0, "the test must exercise an active clip"
 
 
