@@ -12,8 +12,9 @@ step, so N = 8 is exactly the reference's global batch of 1024 sequences.  Each 
 step: forward, backward, gradient reduction, global-norm clip, AdamW, bf16 re-gather.  Synthetic tokens,
 random-init weights (no network for datasets/checkpoints).
 
-The same invocation also measures the second half of BASELINE.json's metric, the 124M ``openwebtext`` config
-(reference src/configs/openwebtext.py:4-22) run as FSDP with the same weak-scaling layout, reported under ``"secondary"``.
+The same invocation also measures the other BASELINE.json configs under ``"secondary"``: the 124M ``openwebtext`` config
+(reference src/configs/openwebtext.py:4-22) run as FSDP with the same weak-scaling layout — the second half of the metric —,
+the 1.5B model at T = 4096 with per-block recompute, and the 1.5B model with MX-fp8 forward GEMMs (``--secondary`` selects).
 
 Two numbers:
   * ``value``  — device-timed (CUDA events, max over ranks) with batches already resident on the GPU;
@@ -52,7 +53,8 @@ def parse():
     p.add_argument("--remat", default="auto", choices=["auto", "block", "none"])
     p.add_argument("--gather-mode", default="auto")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--no-secondary", action="store_true", help="skip the secondary 124M (openwebtext) measurement")
+    p.add_argument("--no-secondary", action="store_true", help="skip the secondary configs")
+    p.add_argument("--secondary", default="124M,seq4096,fp8", help="secondary BASELINE.json configs measured after the headline")
     p.add_argument("--fp8", action="store_true", help="e4m3 forward GEMMs (separate config; the headline number is bf16)")
     p.add_argument("--fp8-format", default="mx", choices=["mx", "row"])
     p.add_argument("--set", action="append", default=[])
@@ -117,10 +119,12 @@ def reference_arm():
     return 0
 
 
-def run_config(args, name: str, steps: int, warmup: int, want_e2e: bool, clocks_on: bool):
+def run_config(args, name: str, steps: int, warmup: int, want_e2e: bool, clocks_on: bool, variant: dict | None = None):
     """Train ``name`` for ``warmup`` + ``steps`` optimizer steps (weak scaling: --seqs-per-gpu sequences per GPU, FSDP over
     all GPUs of the node) and return the measurements of one config as a dict (rank 0) — the headline config and the
-    secondary 124M config go through exactly the same code."""
+    secondary configs go through exactly the same code.  ``variant``: block_size / seqs_per_gpu / remat / fp8 of a BASELINE.json
+    config that differs from the preset (seq-4096 stress, block-scaled fp8)."""
+    variant = variant or {}
     import torch
     import torch.distributed as dist
     from midgpt_b200 import load_config
@@ -132,19 +136,22 @@ def run_config(args, name: str, steps: int, warmup: int, want_e2e: bool, clocks_
 
     cfg = load_config(name)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cfg.batch_size = args.seqs_per_gpu * world
+    seqs_per_gpu = variant.get("seqs_per_gpu", args.seqs_per_gpu)
+    cfg.batch_size = seqs_per_gpu * world
     cfg.g_accum_iters = 1
     cfg.shard_model = True            # BASELINE.json runs every GPU config as FSDP (the 124M preset itself is pure DP)
     cfg.engine.backend = args.backend
     cfg.engine.comm = args.comm
     cfg.engine.gather_mode = args.gather_mode
     cfg.engine.micro_batch_size = args.micro_bs
-    cfg.engine.fp8 = args.fp8
+    cfg.engine.fp8 = args.fp8 or bool(variant.get("fp8"))
     cfg.engine.fp8_format = args.fp8_format
     apply_overrides(cfg, args.set)
+    if "block_size" in variant:
+        cfg.model_config.block_size = variant["block_size"]
     T = cfg.model_config.block_size
     # full activation stash needs ~70 KB/token for the 1.5 B model; keep it when it fits comfortably in 180 GB
-    cfg.engine.remat = "none" if args.remat == "auto" else args.remat
+    cfg.engine.remat = variant.get("remat") or ("none" if args.remat == "auto" else args.remat)
 
     torch.cuda.reset_peak_memory_stats()
     tr = Trainer(cfg, device_type="cuda")
@@ -268,12 +275,27 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
 
     head = run_config(args, args.config, args.steps, args.warmup, not args.no_e2e, True)
+    # The other BASELINE.json configs, measured by the same invocation so that every BENCH / SCALE record carries them:
+    #   124M   reference src/configs/openwebtext.py:4-22, run as FSDP (the other half of "tokens/sec and MFU at 124M & 1.5B")
+    #   seq4096  1.5B, T = 4096, activation-checkpointed (long-context stress; same tokens per GPU: 32 sequences)
+    #   fp8    1.5B with block-scaled (MX e4m3) forward GEMMs -- as far as fp8 exists here (backward GEMMs stay bf16)
     secondary = {}
-    if args.config == "openwebtext_xl" and not args.no_secondary and not args.fp8:
-        # the other half of BASELINE.json's metric ("124M & 1.5B"): reference src/configs/openwebtext.py, as FSDP
-        sec = run_config(args, "openwebtext", max(args.steps, 6), max(args.warmup, 3), not args.no_e2e, False)
-        secondary["openwebtext_124M"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "mfu_nominal_2.25PF", "e2e", "config",
-                                                           "steps", "warmup", "gpu_launches", "comm_exposed_ms", "peak_mem_GB", "final_loss")}
+    keep = ("value", "unit", "ms_per_step", "mfu_nominal_2.25PF", "e2e", "config", "steps", "warmup", "gpu_launches", "comm_exposed_ms",
+            "peak_mem_GB", "final_loss")
+    todo = [] if (args.config != "openwebtext_xl" or args.no_secondary or args.fp8) else [k for k in args.secondary.split(",") if k]
+    specs = {"124M": ("openwebtext_124M", "openwebtext", None, max(args.steps, 6), not args.no_e2e),
+             "seq4096": ("openwebtext_xl_seq4096_remat", "openwebtext_xl", {"block_size": 4096, "seqs_per_gpu": max(1, args.seqs_per_gpu // 4), "remat": "block"}, min(args.steps, 4), False),
+             "fp8": ("openwebtext_xl_fp8_mx_forward", "openwebtext_xl", {"fp8": True}, min(args.steps, 4), False)}
+    for key in todo:
+        label, cfg_name, variant, k_steps, e2e_on = specs[key]
+        try:
+            sec = run_config(args, cfg_name, k_steps, max(args.warmup, 3), e2e_on, False, variant)
+            secondary[label] = {k: sec[k] for k in keep}
+            if key == "fp8":
+                secondary[label]["dtype"] = "fp8-e4m3 MX block-scaled forward GEMMs / bf16 backward"
+                secondary[label]["vs_bf16_headline"] = sec["value"] / head["value"]
+        except Exception as e:      # (deterministic failures hit every rank alike; the headline line is printed regardless)
+            secondary[label] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         fp8 = args.fp8
         out = {"metric": "training throughput, 1.5B openwebtext_xl (tokens/s)" if args.config == "openwebtext_xl" else f"training throughput, {args.config} (tokens/s)"}
