@@ -8,9 +8,10 @@
 //   dgrad     dx = dy · W           A K-major,  B MN-major  (· gelu'(pre) for the MLP up-projection)
 //   wgrad     dW += dyᵀ · x         A MN-major, B MN-major  fp32 output, TMA reduce-add accumulation
 //
-// Roles (320 threads, 1 CTA / SM, grid = #SMs, static persistent tile schedule with M-grouping for L2 reuse):
+// Roles (320 threads, pair kernels 384; 1 CTA / SM, grid = #SMs, static persistent tile schedule with M-grouping for L2 reuse):
 //   warp 0   TMA producer   (one elected lane)
 //   warp 1   TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warp 10-11 (pair kernels) copy warps: the TMA bulk-copy rings of a carried all-gather (see GatherParams); idle otherwise
 //   warp 2-9 epilogue: TMEM -> registers -> epilogue math -> smem staging -> TMA store / reduce-add.
 //            Two warps share each TMEM lane quarter and take alternate column chunks; every warp owns a
 //            32-row staging box and issues its own TMA stores -- no barrier couples the epilogue warps.
@@ -45,15 +46,15 @@ enum Epilogue : int {
 };
 
 // Fused all-gather (all-gather ⊕ GEMM).  The weights of an FSDP unit live in a flat buffer whose `world` equal
-// chunks are owned by different ranks.  A pair-kernel GEMM can CARRY the gather of a whole unit: two extra warps in EVERY CTA
-// (64 threads x 16 outstanding 16-byte NVLink loads = 16 KB in flight per SM, 2.4 MB per GPU -- what the stand-alone pull needs
-// for ~570 GB/s) pull the remote 64 KB segments of the unit from the owners' symmetric shards into the local buffer, in address
-// order starting at the carrier's own B operand, and publish one release-flag per segment.  No SM is taken away from the GEMM
-// (round 1 dedicated ~24 copy-engine CTAs and lost both their tiles and, at 24 x 320 threads, most of the link bandwidth).
-// If the carrier's B operand is itself part of the unit (forward QKV / MLP-in / LM-head GEMM: K-major rows; dgrad: MN-major
-// k-rows) its TMA producers acquire the flags of the segments below the rows they are about to load (a watermark: segments
-// land in address order and every CTA's tiles ascend through B).  Later kernels of the stream need no flags at all: the carrier
-// does not retire before its copy warps have finished.
+// chunks are owned by different ranks.  A pair-kernel GEMM (CARRY instantiations) can CARRY the gather of a whole unit: two extra
+// warps in EVERY CTA each drive a ring of four 4 KB bulk copies -- peer shard -> shared memory -> local unit buffer, the bytes never
+// touch registers -- over the remote 64 KB segments of the unit, in address order starting at the carrier's own B operand, and
+// publish one release-flag per segment.  No SM is taken away from the GEMM (round 1 dedicated ~24 copy-engine CTAs and lost their
+// tiles).  If the carrier's B operand is itself part of the unit (forward QKV / LM-head GEMM: K-major rows; dgrad: MN-major k-rows)
+// its TMA producers acquire the flags of the segments below the rows they are about to load (a watermark: segments land in address
+// order and every CTA's tiles ascend through B).  Later kernels of the stream need no flags at all: the carrier does not retire
+// before its copy warps have finished -- which is how the engine uses it most of the time: the gather of unit l+1 is carried by a
+// GEMM of unit l (parallel/fsdp.py), because NVLink traffic issued next to a saturating tcgen05 mainloop is capped near 140 GB/s.
 struct GatherParams {
   void* peer[8];                    // peer[c] = rank c's bf16 shard (symmetric memory), length chunk_elems
   __nv_bfloat16* local;             // local gathered unit buffer, world * chunk_elems elements
@@ -109,7 +110,7 @@ struct WorkIter {
     left = tiles_mn - full_tiles;
     kps = split > 0 ? (num_k + split - 1) / split : num_k;
     n_items = left * (split > 0 ? (num_k + kps - 1) / kps : 0);       // only the non-empty slices
-    t = worker < 0 ? full_tiles : worker;                             // copy-engine CTAs (worker < 0) own no tiles
+    t = worker < 0 ? full_tiles : worker;                             // (worker < 0: owns no tiles)
     i = worker < 0 ? n_items : worker;
   }
   __host__ MG_DEVICE bool next(int& tile, int& kb0, int& kb1) {
