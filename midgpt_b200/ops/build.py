@@ -41,7 +41,7 @@ def _hash(paths, extra="") -> str:
     h = hashlib.sha256(extra.encode())
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode() + b"\0" + f.read())
+            h.update(os.path.basename(p).encode() + b"\0" + f.read())      # (basename: the digest must not depend on where the repo is checked out)
     return h.hexdigest()
 
 
