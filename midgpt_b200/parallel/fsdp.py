@@ -108,7 +108,7 @@ class FSDPEngine:
             self._gpool_free = [0, 1, 2]
             self._gpool_ready: tp.List[tp.Any] = [None, None, None]     # event: the buffer's last reduction has finished (and zeroed it)
             self._gslot: tp.Dict[int, int] = {}                         # unit -> pool buffer while its backward is in flight
-            self._gtmp = torch.empty(big // self.S, dtype=torch.float32, device=self.device) if True else None
+            self._gtmp = torch.empty(big // self.S, dtype=torch.float32, device=self.device)     # library path: reduce-scatter output before the add
         self._need_gather = True
         self._micro_is_last = True
         self._pending_reduce: tp.List[int] = []
