@@ -48,6 +48,7 @@ class EngineConfig:
     fp8: bool = False              # forward GEMMs of the blocks in e4m3 on the fp8 tensor cores; backward stays bf16
     fp8_format: str = "mx"         # "mx": OCP MX block scaling (UE8M0 per 32 elements, tcgen05 block_scale) | "row": one fp32 scale per row
     seed: int = 0
+    watchdog_s: float = 1800.0     # hang detection: exit(3) if no optimizer step completes for max(this, 20 x median step) seconds; 0 = off
     log_every: int = 20
     ckpt_async: bool = True
 

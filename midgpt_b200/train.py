@@ -174,6 +174,7 @@ class Trainer:
         prof = obs.DebugProfiler(local_rundir or ".", m.rank) if cfg.debug else None
         loader = PinnedBatchLoader(train_s, self.local_seqs, m.device)
         timer = obs.StepTimer(m.device)
+        watchdog = obs.StepWatchdog(local_rundir or None, m.rank, min_timeout_s=cfg.engine.watchdog_s) if cfg.engine.watchdog_s > 0 else None
         total = cfg.max_steps if max_steps is None else min(cfg.max_steps, max_steps)
         try:
             from tqdm import trange
@@ -184,6 +185,8 @@ class Trainer:
         last = {}
         for itr in pbar:
             if itr % cfg.eval_interval == 0:
+                if watchdog:
+                    watchdog.beat(pause=True)          # 2 x 200 evaluation batches are not a hung step
                 tl, vl = self.evaluate(self.train_eval_sampler), self.evaluate(val_s)
                 postfix.update(train_loss=tl, val_loss=vl)
                 logger.log({"loss/train": tl, "loss/val": vl}, step=itr)
@@ -198,6 +201,8 @@ class Trainer:
             if prof:
                 prof.step_end()
             loss_v = loss.item()
+            if watchdog:
+                watchdog.beat()
             if not math.isfinite(loss_v):
                 raise FloatingPointError(f"non-finite loss {loss_v} at step {itr}")
             tps = self.tokens_per_step / (ms * 1e-3)
@@ -217,6 +222,8 @@ class Trainer:
         if hasattr(pbar, "close"):
             pbar.close()
         loader.close()
+        if watchdog:
+            watchdog.close()
         logger.finish()
         if mngr is not None:
             mngr.wait_until_finished()

@@ -119,3 +119,68 @@ class DebugProfiler:
             self._prof.export_chrome_trace(out)
             print(f"[debug] wrote profiler trace {out}")
             self._prof = None
+
+
+class StepWatchdog:
+    """Hang detection (the reference has none: a stuck collective on one host blocks a pod forever).
+
+    ``beat()`` is called once per completed optimizer step.  A daemon thread checks that the next beat arrives within
+    ``max(min_timeout_s, factor x median step time)``; if not it dumps every Python thread's stack (``faulthandler``), writes
+    ``<rundir>/watchdog_rank<r>.txt`` and terminates the process with exit code 3, so that the launcher's retry loop
+    (``gpu retry_launch``, ``scripts/cluster.sh``) relaunches and the run resumes from the last checkpoint.  NCCL's own
+    timeout covers library collectives; this also covers a spinning in-kernel barrier (a peer that died mid-step) and a
+    stalled data loader."""
+
+    def __init__(self, rundir: str | None, rank: int, factor: float = 20.0, min_timeout_s: float = 600.0,
+                 on_timeout: tp.Callable[[str], None] | None = None, poll_s: float = 1.0):
+        import threading
+        self.rundir, self.rank, self.factor, self.min_timeout_s = rundir, rank, factor, min_timeout_s
+        self._on_timeout = on_timeout
+        self._last = time.monotonic()
+        self._durs: tp.List[float] = []
+        self._stop = False
+        self._poll = poll_s
+        self._armed = False                      # armed after the first beat: start-up (init, first eval) is not a step
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def timeout_s(self) -> float:
+        if not self._durs:
+            return self.min_timeout_s
+        med = sorted(self._durs)[len(self._durs) // 2]
+        return max(self.min_timeout_s, self.factor * med)
+
+    def beat(self, pause: bool = False) -> None:
+        """``pause=True``: something long and legitimate is about to happen (evaluation, checkpoint wait): disarm until the next beat."""
+        now = time.monotonic()
+        if self._armed and not pause:
+            self._durs = (self._durs + [now - self._last])[-50:]
+        self._last = now
+        self._armed = not pause
+
+    def close(self) -> None:
+        self._stop = True
+
+    def _run(self) -> None:
+        while not self._stop:
+            time.sleep(self._poll)
+            if not self._armed:
+                continue
+            waited = time.monotonic() - self._last
+            if waited > self.timeout_s():
+                msg = (f"[watchdog] rank {self.rank}: no optimizer step completed for {waited:.0f} s "
+                       f"(limit {self.timeout_s():.0f} s) -- dumping stacks and exiting with code 3")
+                try:
+                    import faulthandler
+                    path = os.path.join(self.rundir or ".", f"watchdog_rank{self.rank}.txt")
+                    with open(path, "w") as f:
+                        f.write(msg + "\n")
+                        faulthandler.dump_traceback(file=f, all_threads=True)
+                except Exception:
+                    pass
+                print(msg, flush=True)
+                if self._on_timeout is not None:
+                    self._on_timeout(msg)
+                    self._stop = True
+                    return
+                os._exit(3)

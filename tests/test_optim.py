@@ -60,3 +60,25 @@ def test_adamw_step_matches_optax_chain_algebra():
     be.adamw_step(p, m, v, torch.zeros_like(p), None, lr=sc.lr, b1=sc.b1, b2=sc.b2, eps=sc.eps,
                   wd_over_lr_peak=sc.wd_over_lr_peak, bc1=sc.bc1, bc2=sc.bc2, grad_scale=1.0)
     assert torch.allclose(p, torch.full_like(p, 1 - cfg.weight_decay))
+
+
+def test_step_watchdog_fires_on_a_hung_step_and_not_on_a_paused_one(tmp_path):
+    """utils/obs.StepWatchdog: a step that does not complete within the limit dumps stacks and calls the timeout action (exit 3
+    in production); evaluation / checkpoint pauses do not count."""
+    import time
+    from midgpt_b200.utils.obs import StepWatchdog
+    fired = []
+    wd = StepWatchdog(str(tmp_path), rank=0, factor=5.0, min_timeout_s=0.3, on_timeout=fired.append, poll_s=0.05)
+    for _ in range(5):
+        time.sleep(0.02)
+        wd.beat()
+    wd.beat(pause=True)
+    time.sleep(0.6)                      # a long evaluation: disarmed
+    assert not fired
+    wd.beat()
+    time.sleep(0.02)
+    wd.beat()
+    time.sleep(0.8)                      # a hung step
+    assert fired and "no optimizer step completed" in fired[0]
+    assert (tmp_path / "watchdog_rank0.txt").exists() and "Thread" in (tmp_path / "watchdog_rank0.txt").read_text()
+    wd.close()
