@@ -98,3 +98,19 @@ def test_hsdp_world4_equals_single():
         assert torch.allclose(torch.tensor(losses), torch.tensor(ref_losses), rtol=1e-5, atol=1e-6)
         for k in ref_state:
             assert torch.allclose(torch.as_tensor(state[k]), ref_state[k], rtol=1e-4, atol=1e-6), k
+
+
+def _run_mesh_from_launcher_env(rank, world):
+    """torchrun --nnodes=2 --nproc-per-node=2 sets LOCAL_WORLD_SIZE=2: the shard group must be one node, replicas across nodes."""
+    import os
+    from midgpt_b200.parallel import dist as D
+    os.environ["LOCAL_WORLD_SIZE"] = "2"
+    mesh = D.make_mesh(True, "cpu")
+    dp = D.make_mesh(False, "cpu")
+    return (mesh.shard_size, mesh.replica_size, mesh.shard_rank, mesh.replica_rank, dp.shard_size, dp.replica_size)
+
+
+def test_shard_group_is_the_node_reported_by_the_launcher():
+    outs = run_distributed(_run_mesh_from_launcher_env, 4)
+    assert [o[:4] for o in outs] == [(2, 2, 0, 0), (2, 2, 1, 0), (2, 2, 0, 1), (2, 2, 1, 1)]
+    assert all(o[4:] == (1, 4) for o in outs)          # shard_model=False: pure DP over all ranks
