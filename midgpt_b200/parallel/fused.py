@@ -17,7 +17,13 @@ With both arenas peer-visible the two FSDP collectives disappear into kernels th
 Ordering uses a device-side all-ranks barrier kernel (system-scope release/acquire flags in a symmetric pad):
 per unit before its pull (all ranks finished that unit's backward), once after all pulls (accumulators may
 be zeroed), once after all pushes (weights visible everywhere).  No NCCL call moves tensor data; NCCL
-carries only the 4-byte Σg² all-reduce.
+carries only the 4-byte Σg² all-reduce (and, across nodes, the replica all-reduce of shard-sized gradients).
+
+``gather_mode="layer"`` (ZeRO-3 weights): only the *shards* are symmetric; the gathered copy of a unit lives in a local pool
+slot and is filled by a GEMM that **carries** the gather (all-gather ⊕ GEMM, csrc/gemm.cu: TMA bulk-copy rings in two extra
+warps of every CTA pull the peers' shards; ``GatherSpec`` is the descriptor).  ``engine.grad_shard`` (ZeRO-2/3 gradients): the
+symmetric gradient arena shrinks to three rotating full-size buffers and ``rs_sumsq`` runs per unit per micro-step in
+accumulate mode (``reduce_scatter_accumulate``).
 """
 from __future__ import annotations
 
@@ -139,7 +145,8 @@ class FusedComm:
         return self.slot_flags[u.pool_slot]
 
     def gather_spec(self, u) -> GatherSpec:
-        """Descriptor consumed by the first K-major GEMM of the unit: that kernel performs the all-gather itself."""
+        """Descriptor for the GEMM that will carry this unit's gather (FSDPEngine decides which one: normally a GEMM of the
+        PREVIOUS unit of the schedule, so that the gather is hidden; the unit's own first GEMM for the first unit of a pass)."""
         flags = self._next_flags(u)
         return GatherSpec(self._peer_shard_ptrs(u), u.lp_full, flags, u.shard, self.slot_calls[u.pool_slot], self.rank, AG_CTAS)
 
