@@ -13,7 +13,11 @@ sharding at src/train.py:172-177) is explicit here:
   memory behaviour for models that need it);
 * weight gradients are accumulated locally in fp32 over all micro-batches of a step and
   reduce-scattered ONCE per unit per step, in fp32, as soon as the unit's last backward is done
-  (X3) — the reference reduce-scatters bf16 every micro-step;
+  (X3) — the reference reduce-scatters bf16 every micro-step; ``engine.grad_shard=True`` restores that
+  behaviour (and its memory: a shard-sized fp32 accumulator plus three rotating full-size buffers);
+* on the in-kernel path, ``gather_mode="layer"`` needs no gather kernel for the blocks: every unit's
+  all-gather is *carried* by a GEMM (csrc/gemm.cu), normally a GEMM of the previous unit of the schedule
+  (``_acquire_fused_layer``: ``__prefetch__`` / ``__gather__`` descriptors handed to the model with the weights);
 * global-norm clip (X8) = per-shard Σg² → one scalar all-reduce → a *device-side* clip factor fed
   to the fused AdamW sweep (K14–K18), so the host never synchronises inside a step.
 
