@@ -158,6 +158,7 @@ class Trainer:
             mngr = CheckpointManager(local_rundir, max_to_keep=1, save_interval_steps=cfg.eval_interval,
                                      async_save=cfg.engine.ckpt_async, remote=remote)
             mngr.sync_from_remote(m)
+            mngr.prepare(eng)
         first_step = 0
         if mngr is not None and mngr.latest_step() is not None:
             extra = mngr.restore(mngr.latest_step(), eng)
