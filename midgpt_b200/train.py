@@ -184,6 +184,7 @@ class Trainer:
             pbar = range(first_step, total)
         postfix: dict = {}
         last = {}
+        stop = _StopRequest(m)             # SIGTERM / SIGUSR1: checkpoint at the next step boundary and leave (preemption, `gpu stop`)
         for itr in pbar:
             if itr % cfg.eval_interval == 0:
                 if watchdog:
@@ -220,6 +221,14 @@ class Trainer:
             if hasattr(pbar, "set_postfix"):
                 pbar.set_postfix(**postfix)
             last.update(loss=loss_v, step=itr, tokens_per_s=tps)
+            if stop.agreed(itr):               # every rank sees the same answer at the same step
+                if mngr is not None and not mngr.should_save(itr):
+                    mngr.save(itr, eng, extra={"sampler": loader.state_dict()}, force=True)
+                if m.is_main:
+                    print(f"[signal] stop requested: checkpoint of step {itr} {'written' if mngr is not None else 'skipped (no rundir)'}; "
+                          f"re-run with the same --rundir to resume at step {itr + 1}", flush=True)
+                last["stopped_at"] = itr
+                break
         if hasattr(pbar, "close"):
             pbar.close()
         loader.close()
@@ -231,6 +240,36 @@ class Trainer:
         if remote is not None and m.is_main:
             remote.push_file("metrics.jsonl")
         return last
+
+
+class _StopRequest:
+    """Cooperative preemption.  SIGTERM / SIGUSR1 on ANY rank sets a flag; every ``every`` steps the ranks agree on it with a
+    one-element MAX all-reduce (a signal delivered to one rank only must not desynchronise the collectives), then the loop
+    writes a forced checkpoint and returns.  The reference's pods are simply killed (``tpu stop`` = ``pkill -9``) and lose
+    everything since the last interval checkpoint."""
+
+    def __init__(self, mesh, every: int = 5):
+        import signal
+        import threading
+        self.mesh, self.every, self.flag = mesh, every, False
+        if threading.current_thread() is threading.main_thread():
+            for sig in (signal.SIGTERM, signal.SIGUSR1):
+                try:
+                    signal.signal(sig, self._handler)
+                except (ValueError, OSError):
+                    pass
+
+    def _handler(self, signum, frame):
+        self.flag = True
+
+    def agreed(self, itr: int) -> bool:
+        if self.mesh.world == 1:
+            return self.flag
+        if itr % self.every:
+            return False
+        t = torch.tensor([1.0 if self.flag else 0.0], device=self.mesh.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return bool(t.item() > 0)
 
 
 def train(config: ExperimentConfig, **kw) -> dict:

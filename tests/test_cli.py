@@ -47,3 +47,30 @@ def test_strip_nproc_both_spellings():
     assert launch.strip_nproc(["--nproc=8", "--config=a"]) == ["--config=a"]
     args = launch.parse_args(launch.strip_nproc(["--config", "shakespeare_char", "--nproc", "2", "--debug"]))
     assert args.config == "shakespeare_char" and args.debug and args.nproc == 0
+
+
+def test_sigterm_checkpoints_and_resume_continues(tmp_path):
+    """Preemption: SIGTERM makes a run write a checkpoint at the next step boundary and exit cleanly; the same command resumes."""
+    import signal
+    import time
+    data = tmp_path / "data"
+    _run(["data/shakespeare_char/prepare.py", "--synthetic", "--out", str(data)])
+    run = tmp_path / "run"
+    cmd = [sys.executable, "launch.py", "--config=shakespeare_char", f"--rundir={run}", "--device=cpu", f"--set=data_dir={data}",
+           "--set=model_config.n_layer=2", "--set=model_config.n_embd=32", "--set=model_config.n_head=2", "--set=model_config.block_size=32",
+           "--set=batch_size=4", "--set=eval_interval=100000", "--set=compute_dtype=float32", "--set=engine.log_every=1", "--max_steps=100000"]
+    env = dict(os.environ, WANDB_MODE="disabled", PYTHONPATH=ROOT)
+    env.pop("RANK", None); env.pop("WORLD_SIZE", None)
+    p = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    metrics = run / "metrics.jsonl"
+    deadline = time.time() + 300
+    while time.time() < deadline and not (metrics.exists() and sum(1 for l in open(metrics) if "loss/optimized" in l) >= 5):
+        time.sleep(0.2)
+    p.send_signal(signal.SIGTERM)
+    out, _ = p.communicate(timeout=120)
+    assert p.returncode == 0, out[-3000:]
+    assert "[signal] stop requested" in out
+    steps = sorted(int(d) for d in os.listdir(run) if d.isdigit())
+    assert len(steps) == 1 and steps[0] >= 4                      # a checkpoint off the (huge) interval: forced by the signal
+    out2 = _run(cmd[1:-1] + [f"--max_steps={steps[0] + 3}"])
+    assert f"resumed from step {steps[0]}" in out2
