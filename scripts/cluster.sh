@@ -12,7 +12,7 @@
 #   gpu health                                ECC / throttle / NVLink error counters of every GPU on every node
 #   gpu reboot                                reboot every node (reference: tpu reboot)
 #   gpu launch <config> <rundir> [flags…]     start training in a detached tmux session on every node (torchrun, 8 ranks/node)
-#   gpu stop                                  kill the tmux session and the exact torchrun process group on every node
+#   gpu stop                                  SIGTERM the run (ranks checkpoint at the next step boundary and exit), then remove the tmux session
 #   gpu maintain <host>                       fault injection: SIGKILL one rank on <host> (run then resumes from the last checkpoint)
 #   gpu retry_launch <config> <rundir>        relaunch until it exits 0 (restart-from-checkpoint recovery loop)
 GPU_REPO_DIR=${GPU_REPO_DIR:-midgpt_b200}
@@ -42,7 +42,9 @@ gpu() {
         ssh $h "cd $GPU_REPO_DIR && tmux new -d -s midgpt \"python -m torch.distributed.run --nnodes=$nnodes --node-rank=$i --nproc-per-node=$GPU_PER_NODE --master-addr=$master --master-port=$GPU_PORT launch.py --config=$config --rundir=$rundir --multihost $* 2>&1 | tee -a launch_$i.log\"" &
         i=$((i+1))
       done; wait ;;
-    stop)   _gpu_each "tmux kill-session -t midgpt 2>/dev/null; true" ;;
+    stop)   # graceful first: SIGTERM to the run's process group -> every rank checkpoints at the next step boundary and exits 0
+            # (Trainer.fit's cooperative preemption), then the session is removed
+            _gpu_each "pid=\$(tmux list-panes -t midgpt -F '#{pane_pid}' 2>/dev/null | head -1); [ -n \"\$pid\" ] && kill -TERM -- -\$(ps -o pgid= \$pid | tr -d ' ') 2>/dev/null; for i in \$(seq ${GPU_STOP_GRACE:-60}); do tmux has-session -t midgpt 2>/dev/null || break; sleep 1; done; tmux kill-session -t midgpt 2>/dev/null; true" ;;
     maintain)
       local host=$1
       ssh $host "pid=\$(nvidia-smi --query-compute-apps=pid --format=csv,noheader | head -1); [ -n \"\$pid\" ] && kill -9 \$pid && echo killed \$pid" ;;
